@@ -1,0 +1,185 @@
+/*
+ * wmd.h - C ABI of libwmd.so: the B200 (sm_100a) wavelet-monodepth decoder hot path.
+ *
+ * The reference (nianticlabs/wavelet-monodepth) has no native/FFI layer: its
+ * boundary for this path is a Python nn.Module / function API built on ATen ops
+ * and the un-vendored pytorch_wavelets package.  Every entry point below names
+ * the reference interface it replaces (paths relative to the reference tree).
+ * The Python mirror of that API lives in wavelet_monodepth_b200/ and reaches
+ * these symbols through ctypes with tensor.data_ptr().
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory unless the
+ *    name says host; all tensors are contiguous fp32 / int32 / uint8;
+ *  - the caller owns every buffer; nothing is allocated, freed or retained;
+ *  - every call is asynchronous on `stream` (a cudaStream_t), re-entrant, and
+ *    never synchronises the device; data-dependent counts stay on the device;
+ *  - return value: WMD_OK (0) or a negative wmd_status; never throws / exits.
+ *
+ * Sparse feature layout ("rows"): active pixels of all samples are enumerated
+ * in (n, y, x) row-major order - the reference's order (KITTI/layers.py:377-378,
+ * 387) extended over the batch - and a feature tensor is a row-major matrix
+ * [rows][ld] (pixel-major, channels contiguous), not the reference's
+ * channel-major (C, M) vector (layers.py:358).  wmd_nchw_to_rows_f32 /
+ * wmd_rows_to_nchw_f32 (with N=1, HW=M) convert at the functional-API boundary.
+ */
+#ifndef WMD_H
+#define WMD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WMD_VERSION 100 /* major*100 + minor */
+
+typedef void* wmd_stream_t; /* cudaStream_t */
+
+typedef enum wmd_status {
+  WMD_OK = 0,
+  WMD_ERR_ARG = -1,         /* null pointer / bad enum */
+  WMD_ERR_SHAPE = -2,       /* unsupported size (odd extent, misaligned leading dim ...) */
+  WMD_ERR_CUDA = -3,        /* a CUDA call failed; see wmd_last_cuda_error() */
+  WMD_ERR_WORKSPACE = -4,   /* workspace too small */
+  WMD_ERR_UNSUPPORTED = -5
+} wmd_status;
+
+enum { WMD_PAD_ZERO = 0, WMD_PAD_REFLECT = 1, WMD_PAD_REPLICATE = 2 };
+enum { WMD_ACT_NONE = 0, WMD_ACT_ELU = 1, WMD_ACT_LRELU = 2, WMD_ACT_SIGMOID = 3 };
+
+int wmd_version(void);
+const char* wmd_status_string(int status);
+/* last cudaError_t recorded by a failing call on this host thread (0 if none) */
+int wmd_last_cuda_error(void);
+/* number of kernels this library has launched on this host thread since load (bench.py's gpu_launches) */
+long long wmd_launch_count(void);
+
+/* ---------------------------------------------------------------- Haar transforms
+ * Replaces pytorch_wavelets.DWTInverse.forward((yl,[yh])) for wave='haar', one level
+ * (call sites KITTI/networks/decoders/depth_decoder.py:164,372,416;
+ * NYUv2/networks/decoders/densedepth_decoder.py:129,137,145,309,357,404) and the
+ * reference's closed form my_iwt_once (depth_decoder.py:225-239).
+ *   ll (N,C,H,W), hf (N,C,3,H,W) [LH,HL,HH] -> out (N,C,2H,2W)
+ *   out[2i+a,2j+b] = 1/2 (ll + (-1)^a lh + (-1)^b hl + (-1)^(a+b) hh), evaluated in
+ *   the dependency's separable order (two 1/sqrt2 passes) so results are bit-equal to it.
+ * Fused consumer (optional, disp may be NULL):
+ *   disp  (N,C,2H,2W) = out * disp_scale, clamped to [0,1] if clamp01   (depth_decoder.py:166)
+ */
+int wmd_idwt_haar_f32(const float* ll, const float* hf, float* out, float* disp, float disp_scale, int clamp01,
+                      int N, int C, int H, int W, wmd_stream_t stream);
+
+/* Replaces one level of pytorch_wavelets.DWTForward.forward (NYUv2/train.py:258,289); also the
+ * adjoint used for the IDWT's backward (KITTI/trainer.py:208-212 trains through inverse_wt).
+ *   x (N,C,H,W), H and W even -> ll (N,C,H/2,W/2), hf (N,C,3,H/2,W/2) */
+int wmd_dwt_haar_f32(const float* x, float* ll, float* hf, int N, int C, int H, int W, wmd_stream_t stream);
+
+/* ---------------------------------------------------------------- threshold + masks
+ * thresh[n] = (max(x_n) - min(x_n)) * ratio over per_sample contiguous floats of sample n.
+ * Replaces `thresh = (yl.max() - yl.min()) * thresh_ratio` (depth_decoder.py:308;
+ * densedepth_decoder.py:316,363), per sample instead of the reference's batch-1.
+ * minmax (2N floats: min,max) is optional.  ws: wmd_range_ws_bytes() bytes, must be
+ * zero-filled before the FIRST use only (the kernel leaves it zeroed). */
+size_t wmd_range_ws_bytes(int N, long long per_sample);
+int wmd_range_thresh_f32(const float* x, int N, long long per_sample, float ratio, float* thresh, float* minmax,
+                         void* ws, size_t ws_bytes, wmd_stream_t stream);
+
+/* The six per-level pixel sets (depth_decoder.py:305-319, densedepth_decoder.py:316-322):
+ *   S0 = max_band |yh| > thresh[n]  (strict; thresh == NULL -> all ones, the reference's level-4 case :305-306)
+ *   S1 = dilate3(S0)  S2 = dilate5(S0)                  low resolution  (N,H,W)
+ *   S5 = up2(S0)  S4 = dilate3(S5)  S3 = dilate5(S5)    high resolution (N,2H,2W)
+ * yh is (N,3,H,W).  Any output pointer may be NULL.  Masks are 0/1 bytes. */
+int wmd_level_masks(const float* yh, const float* thresh, uint8_t* s0, uint8_t* s1, uint8_t* s2, uint8_t* s3,
+                    uint8_t* s4, uint8_t* s5, int N, int H, int W, wmd_stream_t stream);
+
+/* Replaces mask2idxmap + mask2yx (KITTI/layers.py:371-389) for a whole batch, without the
+ * reference's host sync (layers.py:385):
+ *   idxmap  (N,H,W) int32 : running row index over the batch, -1 where inactive   [nullable]
+ *   pixels  (<= N*H*W) int32 : linear pixel index (n*H + y)*W + x of each active pixel [nullable]
+ *   offsets (N+1) int32 : offsets[n] = rows before sample n, offsets[N] = total rows */
+size_t wmd_compact_ws_bytes(int N, int H, int W);
+int wmd_compact_mask(const uint8_t* mask, int32_t* idxmap, int32_t* pixels, int32_t* offsets, int N, int H, int W,
+                     void* ws, size_t ws_bytes, wmd_stream_t stream);
+
+/* out[p] = gate[p] ? (idxmap ? idxmap[p] : p) : -1   for p < count.
+ * The fused form of sparse_select (layers.py:337-362): re-indexing onto a subset is a map rewrite. */
+int wmd_gate_map(const uint8_t* gate, const int32_t* idxmap, int32_t* out, long long count, wmd_stream_t stream);
+
+/* ---------------------------------------------------------------- layout helpers
+ * (N,C,HW) <-> (N,HW,ld) batched transposes (ld >= C; pad columns are zero-filled on the way in).
+ * Used for NCHW encoder features -> pixel-major rows, and for the reference's channel-major
+ * wire format (layers.py:358) at the functional API. */
+int wmd_nchw_to_rows_f32(const float* src, float* dst, int N, int C, long long HW, int ld, wmd_stream_t stream);
+int wmd_rows_to_nchw_f32(const float* src, float* dst, int N, int C, long long HW, int ld, wmd_stream_t stream);
+/* rows at an active-pixel list <-> dense NCHW (x[mask] selection, depth_decoder.py:347; make_result, layers.py:365-368) */
+int wmd_gather_rows_nchw_f32(const float* src_nchw, float* rows, int ld, int C, const int32_t* pixels,
+                             const int32_t* count, int max_rows, int N, int H, int W, wmd_stream_t stream);
+int wmd_scatter_rows_nchw_f32(const float* rows, int ld, int C, const int32_t* pixels, const int32_t* count,
+                              int max_rows, float* dst_nchw, int N, int H, int W, wmd_stream_t stream);
+/* conv weight (Cout,Cin,kh,kw) -> packed [kh*kw][Cin][ldw] (ldw >= Cout, multiple of 4, pad zero) */
+int wmd_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, int taps, int ldw, wmd_stream_t stream);
+
+/* ---------------------------------------------------------------- gather-GEMM convolution
+ * Replaces sparse_conv3x3 / sparse_conv1x1 / sparse_upsample / sparse_select (KITTI/layers.py:337-508,
+ * NYUv2/networks/layers.py:82-223) and, with pixels == NULL, the dense Conv3x3/ConvBlock/Conv1x1 layers
+ * (KITTI/layers.py:120-173) of the decoder.  For each output row m (pixel p = pixels[m], or m itself):
+ *   y[m, :] = act( bias + sum_{tap, c} in(p + tap)[c] * w[tap][c][:] )
+ * where in(q) is the channel concatenation of
+ *   source 0: x0[ row0(q), 0:c0 ]  with row0(q) = map0[n, qy>>shift0, qx>>shift0]  (map0 NULL: that pixel's
+ *             linear index; taps==1 && map0==NULL: row m itself), zero if row0 < 0        [sparse_select/upsample]
+ *   source 1: x1[ (n*H+qy)*W+qx, 0:c1 ]  (dense pixel-major skip map at output resolution)  [skip concat, :500]
+ * and in(q) = 0 entirely if gate != NULL and gate[q] == 0, or q is out of the image under WMD_PAD_ZERO.
+ * q is mapped into the image by pad_mode exactly as padding the index map does (layers.py:444).
+ */
+typedef struct wmd_conv_desc {
+  int32_t N, H, W;          /* output grid */
+  const float* x0;          /* source 0 rows [*][ld0] */
+  int32_t c0, ld0;
+  const int32_t* map0;      /* (N, H>>shift0, W>>shift0) or NULL */
+  int32_t shift0;           /* 0 or 1 */
+  const float* x1;          /* source 1 rows [N*H*W][ld1] or NULL */
+  int32_t c1, ld1;
+  const uint8_t* gate;      /* (N,H,W) or NULL */
+  const float* w;           /* packed [taps][c0+c1][ldw] */
+  const float* bias;        /* [cout] or NULL */
+  int32_t cout, ldw, taps;  /* taps: 1 or 9 */
+  int32_t pad_mode;         /* WMD_PAD_* */
+  const int32_t* pixels;    /* active output list or NULL (= every pixel) */
+  const int32_t* count;     /* device row count (with pixels) */
+  int32_t max_rows;         /* capacity of y / upper bound of *count */
+  float* y;                 /* rows [max_rows][ldy] */
+  int32_t ldy;
+  int32_t act;              /* WMD_ACT_* */
+  float act_param;          /* LeakyReLU slope */
+} wmd_conv_desc;
+
+int wmd_conv_rows_f32(const wmd_conv_desc* d, wmd_stream_t stream);
+
+/* ---------------------------------------------------------------- coefficient heads (few output channels)
+ * The 3x3 stage of the wavelet heads (depth_decoder.py:104-120,126-136,242-290; NYU wave convs
+ * densedepth_decoder.py:104-115) on pixel-major rows `t`, scattered to a dense NCHW tensor:
+ *   a = conv3x3(t[:, off_a:off_a+c]; wa, ba)   b = conv3x3(t[:, off_b:off_b+c]; wb, bb)   (off_b < 0: single head)
+ *   out[n, :, y, x] = scale * (act(a) - act(b))     or   scale * act(a)
+ * out must be zero-filled by the caller when pixels != NULL (the reference's make_result, layers.py:473-478).
+ */
+typedef struct wmd_head_desc {
+  int32_t N, H, W;
+  const float* t;
+  int32_t ld, c, off_a, off_b;
+  const int32_t* map;       /* (N,H,W) row of each pixel, -1 inactive; NULL = linear pixel index */
+  const float* wa; const float* ba;   /* packed [9][c][cout], bias [cout] */
+  const float* wb; const float* bb;
+  int32_t cout;             /* 1..4 */
+  int32_t pad_mode, act;
+  float scale;
+  const int32_t* pixels; const int32_t* count; int32_t max_rows;
+  float* out;               /* (N,cout,H,W) */
+} wmd_head_desc;
+
+int wmd_head_conv3x3_f32(const wmd_head_desc* d, wmd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WMD_H */

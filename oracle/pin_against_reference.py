@@ -287,6 +287,22 @@ def pin_known_answers(save):
         json.dump(kat, f, indent=1, sort_keys=True)
 
 
+def pin_state_dicts():
+    """Record the reference modules' state-dict keys/shapes: the checkpoint-compatibility contract."""
+    rec = {}
+    _, dec = import_reference("KITTI")
+    for name in ("DepthDecoder", "DepthWaveProgressiveDecoder", "SparseDepthWaveProgressiveDecoder"):
+        m = getattr(dec, name)(np.array(synth.RESNET18_CH))
+        rec["kitti." + name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    _, dec = import_reference("NYUv2")
+    for name in ("DecoderWave", "SparseDecoderWave"):
+        m = silence(getattr(dec, name), enc_features=list(synth.DENSENET161_CH), decoder_width=0.5)
+        rec["nyu." + name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(GOLDEN, "state_dict_keys.json"), "w") as f:
+        json.dump(rec, f, indent=0, sort_keys=False)
+    print("  recorded state-dict contracts of %d reference modules" % len(rec))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-kat", action="store_true", help="skip the two full-size op-count runs (~10 s)")
@@ -304,6 +320,7 @@ def main():
     layers = pin_kitti(save)
     pin_sparse_ops(layers, save)
     pin_nyu(save)
+    pin_state_dicts()
     if not args.skip_kat:
         pin_known_answers(save)
     print("golden vectors written to", GOLDEN)

@@ -1,0 +1,81 @@
+"""CPU: host-side mirror of the reference API - module structure, state-dict contract, loud failure off-GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from wavelet_monodepth_b200 import kitti_decoders as kd
+from wavelet_monodepth_b200 import nyu_decoders as nd
+from wavelet_monodepth_b200 import synth, wavelets
+from wavelet_monodepth_b200._lib import WmdError
+
+from helpers import GOLDEN
+
+CONTRACT = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+
+
+@pytest.mark.parametrize("name", ["DepthDecoder", "DepthWaveProgressiveDecoder", "SparseDepthWaveProgressiveDecoder"])
+def test_kitti_state_dict_contract(name):
+    mod = getattr(kd, name)(np.array(synth.RESNET18_CH))
+    got = {k: list(v.shape) for k, v in mod.state_dict().items()}
+    assert got == CONTRACT["kitti." + name]
+    assert list(got) == list(CONTRACT["kitti." + name])          # same order too
+
+
+@pytest.mark.parametrize("name", ["DecoderWave", "SparseDecoderWave"])
+def test_nyu_state_dict_contract(name):
+    mod = getattr(nd, name)(enc_features=list(synth.DENSENET161_CH), decoder_width=0.5)
+    got = {k: list(v.shape) for k, v in mod.state_dict().items()}
+    assert got == CONTRACT["nyu." + name]
+
+
+def test_convs_hold_only_conv_parameters():
+    """KITTI/trainer.py:74-75 feeds decoder.convs to pyt_utils.group_weight, which asserts exactly this."""
+    mod = kd.DepthWaveProgressiveDecoder(np.array(synth.RESNET18_CH))
+    assert [k for k in mod.convs][:5] == [("upconv", 4, 0), ("upconv", 4, 1), ("waveconv", 4, 0), ("waveconv", 4, 1),
+                                          ("waveconv", 4, -1)]
+    for v in mod.convs.values():
+        n_conv = sum(len(list(m.parameters(recurse=False))) for m in v.modules() if isinstance(m, nn.Conv2d))
+        assert n_conv == len(list(v.parameters()))
+    assert len(mod.decoder) == 17
+
+
+def test_wavelet_modules_keep_dependency_api():
+    idwt = wavelets.IDWT(wave="haar", mode="zero")
+    dwt = wavelets.DWT(J=4, wave="haar", mode="reflect")
+    assert set(idwt.state_dict()) == {"g0_col", "g1_col", "g0_row", "g1_row"}
+    assert set(dwt.state_dict()) == {"h0_col", "h1_col", "h0_row", "h1_row"}
+    assert idwt.g0_col.shape == (1, 1, 2, 1) and idwt.g1_row.shape == (1, 1, 1, 2)
+    with pytest.raises(NotImplementedError):
+        wavelets.DWTInverse(wave="db2")
+
+
+def test_cpu_tensors_fail_loudly():
+    """No CPU fallback: the product path refuses host tensors instead of silently computing elsewhere."""
+    mod = kd.SparseDepthWaveProgressiveDecoder(np.array((8, 8, 16, 32, 64)))
+    feats = [torch.zeros(s) for s in synth.kitti_feature_shapes(1, 64, 96, (8, 8, 16, 32, 64))]
+    with pytest.raises(WmdError):
+        mod(feats, 0.05)
+    with pytest.raises(WmdError):
+        wavelets.IDWT(wave="haar")((torch.zeros(1, 1, 4, 4), [torch.zeros(1, 1, 3, 4, 4)]))
+
+
+def test_product_never_imports_the_oracle():
+    import re
+    root = os.path.dirname(os.path.abspath(kd.__file__))
+    for fn in os.listdir(root):
+        if fn.endswith(".py"):
+            src = open(os.path.join(root, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_synthetic_generators_are_deterministic():
+    a = synth.blocky_features([(2, 3, 8, 12)], seed=4, cell=4)[0]
+    b = synth.blocky_features([(1, 3, 8, 12)], seed=5, cell=4)[0]
+    assert torch.equal(a[1:], b)                      # sample n of a batch == stream seed+n
+    sd = synth.random_state_dict({"c.weight": (4, 3, 3, 3), "c.bias": (4,)}, seed=1)
+    assert abs(float(sd["c.weight"].abs().max())) <= 1 / np.sqrt(27) + 1e-7
+    assert float(sd["c.weight"].double().sum()) == pytest.approx(-0.3225997, abs=1e-5)   # frozen MT19937 stream

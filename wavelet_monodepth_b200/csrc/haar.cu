@@ -1,0 +1,145 @@
+// K1 / K2: one-level 2-D Haar synthesis (IDWT) and analysis (DWT), fp32, NCHW planes.
+//
+// HBM-bound streaming kernels: every coefficient is read once and every output written once
+// (algorithmic bytes 32*N*C*H*W for the IDWT, +16*N*C*H*W with the fused disp plane), 128-bit
+// coalesced accesses, no shared memory (no reuse to exploit), grid-stride over a grid sized in
+// multiples of the SM count.  The arithmetic follows the dependency's separable evaluation order
+// (oracle/haar.py) with explicit roundings (no FMA contraction) so results are bit-identical to it.
+#include "common.cuh"
+
+namespace wmd {
+
+#define WMD_S 0.70710678118654752440f
+
+struct Quad { float y00, y01, y10, y11; };
+
+__device__ __forceinline__ Quad haar_synth(float ll, float lh, float hl, float hh) {
+  // column pass (height): lo = g0*ll + g1*lh, hi = g0*hl + g1*hh ; then row pass (width)
+  const float sll = __fmul_rn(WMD_S, ll), slh = __fmul_rn(WMD_S, lh);
+  const float shl = __fmul_rn(WMD_S, hl), shh = __fmul_rn(WMD_S, hh);
+  const float lo0 = __fadd_rn(sll, slh), lo1 = __fsub_rn(sll, slh);   // rows 2i, 2i+1 of the low band
+  const float hi0 = __fadd_rn(shl, shh), hi1 = __fsub_rn(shl, shh);
+  const float a0 = __fmul_rn(WMD_S, lo0), b0 = __fmul_rn(WMD_S, hi0);
+  const float a1 = __fmul_rn(WMD_S, lo1), b1 = __fmul_rn(WMD_S, hi1);
+  Quad q;
+  q.y00 = __fadd_rn(a0, b0); q.y01 = __fsub_rn(a0, b0);
+  q.y10 = __fadd_rn(a1, b1); q.y11 = __fsub_rn(a1, b1);
+  return q;
+}
+
+__device__ __forceinline__ float disp_of(float v, float scale, int clamp01) {
+  v = __fmul_rn(v, scale);
+  return clamp01 ? fminf(fmaxf(v, 0.f), 1.f) : v;
+}
+
+// VEC: W even; one thread = two coefficient columns = a 2x4 output patch (two float4 stores per plane).
+template <bool VEC>
+__global__ void __launch_bounds__(256) idwt_haar_kernel(const float* __restrict__ ll, const float* __restrict__ hf,
+                                                        float* __restrict__ out, float* __restrict__ disp,
+                                                        float disp_scale, int clamp01, long long planes, int H, int W) {
+  const long long HW = static_cast<long long>(H) * W;
+  const int Wv = VEC ? (W >> 1) : W;
+  const long long total = planes * H * Wv;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += step) {
+    const int jv = static_cast<int>(idx % Wv);
+    const long long t = idx / Wv;
+    const int i = static_cast<int>(t % H);
+    const long long p = t / H;
+    const long long cofs = static_cast<long long>(i) * W + (VEC ? 2 * jv : jv);
+    const float* pl = ll + p * HW + cofs;
+    const float* ph = hf + p * 3 * HW + cofs;
+    const long long oofs = p * 4 * HW + static_cast<long long>(2 * i) * (2 * W) + (VEC ? 4 * jv : 2 * jv);
+    if (VEC) {
+      const float2 vll = __ldg(reinterpret_cast<const float2*>(pl));
+      const float2 vlh = __ldg(reinterpret_cast<const float2*>(ph));
+      const float2 vhl = __ldg(reinterpret_cast<const float2*>(ph + HW));
+      const float2 vhh = __ldg(reinterpret_cast<const float2*>(ph + 2 * HW));
+      const Quad q0 = haar_synth(vll.x, vlh.x, vhl.x, vhh.x);
+      const Quad q1 = haar_synth(vll.y, vlh.y, vhl.y, vhh.y);
+      const float4 r0 = make_float4(q0.y00, q0.y01, q1.y00, q1.y01);
+      const float4 r1 = make_float4(q0.y10, q0.y11, q1.y10, q1.y11);
+      *reinterpret_cast<float4*>(out + oofs) = r0;
+      *reinterpret_cast<float4*>(out + oofs + 2 * W) = r1;
+      if (disp) {
+        *reinterpret_cast<float4*>(disp + oofs) =
+            make_float4(disp_of(r0.x, disp_scale, clamp01), disp_of(r0.y, disp_scale, clamp01),
+                        disp_of(r0.z, disp_scale, clamp01), disp_of(r0.w, disp_scale, clamp01));
+        *reinterpret_cast<float4*>(disp + oofs + 2 * W) =
+            make_float4(disp_of(r1.x, disp_scale, clamp01), disp_of(r1.y, disp_scale, clamp01),
+                        disp_of(r1.z, disp_scale, clamp01), disp_of(r1.w, disp_scale, clamp01));
+      }
+    } else {
+      const Quad q = haar_synth(__ldg(pl), __ldg(ph), __ldg(ph + HW), __ldg(ph + 2 * HW));
+      out[oofs] = q.y00; out[oofs + 1] = q.y01;
+      out[oofs + 2 * W] = q.y10; out[oofs + 2 * W + 1] = q.y11;
+      if (disp) {
+        disp[oofs] = disp_of(q.y00, disp_scale, clamp01);
+        disp[oofs + 1] = disp_of(q.y01, disp_scale, clamp01);
+        disp[oofs + 2 * W] = disp_of(q.y10, disp_scale, clamp01);
+        disp[oofs + 2 * W + 1] = disp_of(q.y11, disp_scale, clamp01);
+      }
+    }
+  }
+}
+
+// x (planes,H,W) with H,W even -> ll (planes,H/2,W/2), hf (planes,3,H/2,W/2).  One thread per output pixel.
+__global__ void __launch_bounds__(256) dwt_haar_kernel(const float* __restrict__ x, float* __restrict__ ll,
+                                                       float* __restrict__ hf, long long planes, int H, int W) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long HWo = static_cast<long long>(Ho) * Wo;
+  const long long total = planes * HWo;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += step) {
+    const int j = static_cast<int>(idx % Wo);
+    const long long t = idx / Wo;
+    const int i = static_cast<int>(t % Ho);
+    const long long p = t / Ho;
+    const float* px = x + p * static_cast<long long>(H) * W + static_cast<long long>(2 * i) * W + 2 * j;
+    const float2 r0 = __ldg(reinterpret_cast<const float2*>(px));
+    const float2 r1 = __ldg(reinterpret_cast<const float2*>(px + W));
+    // row pass (width): lo = s*x0 + s*x1, hi = s*x0 - s*x1
+    const float lo0 = __fadd_rn(__fmul_rn(WMD_S, r0.x), __fmul_rn(WMD_S, r0.y));
+    const float hi0 = __fsub_rn(__fmul_rn(WMD_S, r0.x), __fmul_rn(WMD_S, r0.y));
+    const float lo1 = __fadd_rn(__fmul_rn(WMD_S, r1.x), __fmul_rn(WMD_S, r1.y));
+    const float hi1 = __fsub_rn(__fmul_rn(WMD_S, r1.x), __fmul_rn(WMD_S, r1.y));
+    // column pass (height)
+    const long long o = static_cast<long long>(i) * Wo + j;
+    ll[p * HWo + o] = __fadd_rn(__fmul_rn(WMD_S, lo0), __fmul_rn(WMD_S, lo1));
+    float* ph = hf + p * 3 * HWo + o;
+    ph[0] = __fsub_rn(__fmul_rn(WMD_S, lo0), __fmul_rn(WMD_S, lo1));        // LH: low along width, high along height
+    ph[HWo] = __fadd_rn(__fmul_rn(WMD_S, hi0), __fmul_rn(WMD_S, hi1));      // HL
+    ph[2 * HWo] = __fsub_rn(__fmul_rn(WMD_S, hi0), __fmul_rn(WMD_S, hi1));  // HH
+  }
+}
+
+}  // namespace wmd
+
+extern "C" int wmd_idwt_haar_f32(const float* ll, const float* hf, float* out, float* disp, float disp_scale,
+                                 int clamp01, int N, int C, int H, int W, wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(ll && hf && out, WMD_ERR_ARG);
+  WMD_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0, WMD_ERR_SHAPE);
+  const long long planes = static_cast<long long>(N) * C;
+  if (planes == 0) return WMD_OK;
+  const bool vec = (W % 2) == 0;
+  const long long work = planes * H * (vec ? W / 2 : W);
+  const int grid = stride_grid(work, 256);
+  if (vec)
+    idwt_haar_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(ll, hf, out, disp, disp_scale, clamp01, planes, H, W);
+  else
+    idwt_haar_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(ll, hf, out, disp, disp_scale, clamp01, planes, H, W);
+  return launched();
+}
+
+extern "C" int wmd_dwt_haar_f32(const float* x, float* ll, float* hf, int N, int C, int H, int W,
+                                wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(x && ll && hf, WMD_ERR_ARG);
+  WMD_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, WMD_ERR_SHAPE);
+  const long long planes = static_cast<long long>(N) * C;
+  if (planes == 0) return WMD_OK;
+  const long long work = planes * (H / 2) * (W / 2);
+  dwt_haar_kernel<<<stride_grid(work, 256), 256, 0, as_stream(stream)>>>(x, ll, hf, planes, H, W);
+  return launched();
+}

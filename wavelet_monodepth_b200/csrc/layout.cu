@@ -1,0 +1,202 @@
+// Layout helpers: NCHW <-> pixel-major rows (batched tiled transposes through shared memory so both
+// sides are coalesced), row gather/scatter at an active-pixel list, conv-weight packing.
+#include "common.cuh"
+
+namespace wmd {
+
+constexpr int kTT = 32;
+
+// src (N, C, HW) -> dst (N, HW, ld); columns C..ld-1 zero-filled.
+__global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           int C, long long HW, int ld) {
+  __shared__ float tile[kTT][kTT + 1];
+  const int n = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * kTT;
+  const int c0 = blockIdx.y * kTT;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* s = src + static_cast<long long>(n) * C * HW;
+  float* d = dst + static_cast<long long>(n) * HW * ld;
+  for (int r = ty; r < kTT; r += 8) {
+    const int c = c0 + r;
+    const long long p = p0 + tx;
+    tile[r][tx] = (c < C && p < HW) ? __ldg(s + static_cast<long long>(c) * HW + p) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < kTT; r += 8) {
+    const long long p = p0 + r;
+    const int c = c0 + tx;
+    if (p < HW && c < ld) d[p * ld + c] = tile[tx][r];
+  }
+}
+
+// src (N, HW, ld) -> dst (N, C, HW)
+__global__ void __launch_bounds__(256) rows_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           int C, long long HW, int ld) {
+  __shared__ float tile[kTT][kTT + 1];
+  const int n = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * kTT;
+  const int c0 = blockIdx.y * kTT;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* s = src + static_cast<long long>(n) * HW * ld;
+  float* d = dst + static_cast<long long>(n) * C * HW;
+  for (int r = ty; r < kTT; r += 8) {
+    const long long p = p0 + r;
+    const int c = c0 + tx;
+    tile[r][tx] = (p < HW && c < C) ? __ldg(s + p * ld + c) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < kTT; r += 8) {
+    const int c = c0 + r;
+    const long long p = p0 + tx;
+    if (c < C && p < HW) d[static_cast<long long>(c) * HW + p] = tile[tx][r];
+  }
+}
+
+// rows[m][c] = src[n, c, y, x] for the m-th listed pixel.  One warp handles 32 consecutive rows of one
+// 32-channel slab through a shared tile so the NCHW side is read along x and the row side written along c.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, float* __restrict__ rows,
+                                                          int ld, int C, const int32_t* __restrict__ pixels,
+                                                          const int32_t* __restrict__ count, int max_rows,
+                                                          long long HW) {
+  __shared__ float tile[kTT][kTT + 1];
+  __shared__ int32_t pix[kTT];
+  const int M = count ? min(*count, max_rows) : max_rows;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ctiles = (C + kTT - 1) / kTT;
+  const long long tiles = static_cast<long long>((M + kTT - 1) / kTT) * ctiles;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int m0 = static_cast<int>(t / ctiles) * kTT;
+    const int c0 = static_cast<int>(t % ctiles) * kTT;
+    if (threadIdx.x < kTT) {
+      const int mm = m0 + static_cast<int>(threadIdx.x);
+      pix[threadIdx.x] = mm < M ? (pixels ? pixels[mm] : mm) : -1;
+    }
+    __syncthreads();
+    for (int r = ty; r < kTT; r += 8) {   // r: channel within slab, tx: row within tile
+      const int c = c0 + r;
+      const int32_t p = pix[tx];
+      float v = 0.f;
+      if (p >= 0 && c < C) {
+        const long long n = p / HW, rem = p % HW;
+        v = __ldg(src + (n * C + c) * HW + rem);
+      }
+      tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < kTT; r += 8) {   // r: row within tile, tx: channel
+      const int m = m0 + r, c = c0 + tx;
+      if (m < M && c < C) rows[static_cast<long long>(m) * ld + c] = tile[tx][r];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ rows, int ld, int C,
+                                                           const int32_t* __restrict__ pixels,
+                                                           const int32_t* __restrict__ count, int max_rows,
+                                                           float* __restrict__ dst, long long HW) {
+  __shared__ float tile[kTT][kTT + 1];
+  __shared__ int32_t pix[kTT];
+  const int M = count ? min(*count, max_rows) : max_rows;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ctiles = (C + kTT - 1) / kTT;
+  const long long tiles = static_cast<long long>((M + kTT - 1) / kTT) * ctiles;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int m0 = static_cast<int>(t / ctiles) * kTT;
+    const int c0 = static_cast<int>(t % ctiles) * kTT;
+    if (threadIdx.x < kTT) {
+      const int mm = m0 + static_cast<int>(threadIdx.x);
+      pix[threadIdx.x] = mm < M ? (pixels ? pixels[mm] : mm) : -1;
+    }
+    __syncthreads();
+    for (int r = ty; r < kTT; r += 8) {   // r: row within tile, tx: channel
+      const int m = m0 + r, c = c0 + tx;
+      tile[r][tx] = (m < M && c < C) ? __ldg(rows + static_cast<long long>(m) * ld + c) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < kTT; r += 8) {   // r: channel, tx: row
+      const int c = c0 + r;
+      const int32_t p = pix[tx];
+      if (p >= 0 && c < C) {
+        const long long n = p / HW, rem = p % HW;
+        dst[(n * C + c) * HW + rem] = tile[tx][r];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// w (Cout, Cin, taps) -> packed [taps][Cin][ldw]
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int Cout, int Cin,
+                                   int taps, int ldw) {
+  const long long total = static_cast<long long>(taps) * Cin * ldw;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int co = static_cast<int>(i % ldw);
+    const long long r = i / ldw;
+    const int ci = static_cast<int>(r % Cin);
+    const int tap = static_cast<int>(r / Cin);
+    packed[i] = co < Cout ? __ldg(w + (static_cast<long long>(co) * Cin + ci) * taps + tap) : 0.f;
+  }
+}
+
+}  // namespace wmd
+
+extern "C" int wmd_nchw_to_rows_f32(const float* src, float* dst, int N, int C, long long HW, int ld,
+                                    wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(src && dst, WMD_ERR_ARG);
+  WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
+  if (N == 0) return WMD_OK;
+  dim3 grid(ceil_div(HW, kTT), ceil_div(ld, kTT), N);
+  WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
+  nchw_to_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, HW, ld);
+  return launched();
+}
+
+extern "C" int wmd_rows_to_nchw_f32(const float* src, float* dst, int N, int C, long long HW, int ld,
+                                    wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(src && dst, WMD_ERR_ARG);
+  WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
+  if (N == 0) return WMD_OK;
+  dim3 grid(ceil_div(HW, kTT), ceil_div(C, kTT), N);
+  WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
+  rows_to_nchw_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, HW, ld);
+  return launched();
+}
+
+extern "C" int wmd_gather_rows_nchw_f32(const float* src_nchw, float* rows, int ld, int C, const int32_t* pixels,
+                                        const int32_t* count, int max_rows, int N, int H, int W,
+                                        wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(src_nchw && rows, WMD_ERR_ARG);
+  WMD_REQUIRE(C > 0 && ld >= C && N > 0 && H > 0 && W > 0 && max_rows >= 0, WMD_ERR_SHAPE);
+  if (max_rows == 0) return WMD_OK;
+  const long long tiles = static_cast<long long>(ceil_div(max_rows, kTT)) * ceil_div(C, kTT);
+  gather_rows_kernel<<<stride_grid(tiles * 256, 256, 4), 256, 0, as_stream(stream)>>>(
+      src_nchw, rows, ld, C, pixels, count, max_rows, static_cast<long long>(H) * W);
+  return launched();
+}
+
+extern "C" int wmd_scatter_rows_nchw_f32(const float* rows, int ld, int C, const int32_t* pixels, const int32_t* count,
+                                         int max_rows, float* dst_nchw, int N, int H, int W, wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(rows && dst_nchw, WMD_ERR_ARG);
+  WMD_REQUIRE(C > 0 && ld >= C && N > 0 && H > 0 && W > 0 && max_rows >= 0, WMD_ERR_SHAPE);
+  if (max_rows == 0) return WMD_OK;
+  const long long tiles = static_cast<long long>(ceil_div(max_rows, kTT)) * ceil_div(C, kTT);
+  scatter_rows_kernel<<<stride_grid(tiles * 256, 256, 4), 256, 0, as_stream(stream)>>>(
+      rows, ld, C, pixels, count, max_rows, dst_nchw, static_cast<long long>(H) * W);
+  return launched();
+}
+
+extern "C" int wmd_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, int taps, int ldw,
+                                        wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(w && packed, WMD_ERR_ARG);
+  WMD_REQUIRE(Cout > 0 && Cin > 0 && taps > 0 && ldw >= Cout, WMD_ERR_SHAPE);
+  const long long total = static_cast<long long>(taps) * Cin * ldw;
+  pack_weight_kernel<<<stride_grid(total, 256), 256, 0, as_stream(stream)>>>(w, packed, Cout, Cin, taps, ldw);
+  return launched();
+}

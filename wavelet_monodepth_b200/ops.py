@@ -1,0 +1,285 @@
+"""Tensor-level wrappers over the C ABI (include/wmd.h).
+
+PyTorch is used for device memory and streams only: every function allocates
+its outputs with torch, passes raw pointers to libwmd on torch's current stream
+and returns tensors.  No arithmetic happens in torch here.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_ELU, ACT_LRELU, ACT_NONE, ACT_SIGMOID, PAD_REFLECT, PAD_REPLICATE, PAD_ZERO  # noqa: F401
+
+_f32 = torch.float32
+_i32 = torch.int32
+_u8 = torch.uint8
+
+
+def _dense(t, dtype=_f32):
+    """Contiguous, 16-byte aligned tensor of `dtype` (copies only if needed)."""
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+class _Scratch:
+    """Per-device scratch buffers for the range / compaction kernels."""
+
+    def __init__(self):
+        self.range_ws = {}
+        self.compact_ws = {}
+
+    def range(self, device, nbytes):
+        buf = self.range_ws.get(device)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.zeros(max(nbytes, 1 << 16), dtype=_u8, device=device)   # zeroed once; kernel keeps it zero
+            self.range_ws[device] = buf
+        return buf
+
+    def compact(self, device, nbytes):
+        buf = self.compact_ws.get(device)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 16), dtype=_u8, device=device)
+            self.compact_ws[device] = buf
+        return buf
+
+
+_scratch = _Scratch()
+
+
+# --------------------------------------------------------------------------- Haar
+def idwt_haar(ll, hf, disp_scale=None, clamp01=False):
+    """ll (N,C,H,W), hf (N,C,3,H,W) -> out (N,C,2H,2W) [, disp = clamp?(out*disp_scale)]."""
+    lib = _lib.load()
+    ll, hf = _dense(ll), _dense(hf)
+    n, c, h, w = ll.shape
+    if tuple(hf.shape) != (n, c, 3, h, w):
+        raise _lib.WmdError("idwt_haar: hf shape %s does not match ll %s" % (tuple(hf.shape), tuple(ll.shape)))
+    out = torch.empty((n, c, 2 * h, 2 * w), dtype=_f32, device=ll.device)
+    disp = torch.empty_like(out) if disp_scale is not None else None
+    rc = lib.wmd_idwt_haar_f32(_lib.ptr(ll), _lib.ptr(hf), _lib.ptr(out), _lib.ptr(disp),
+                               float(disp_scale if disp_scale is not None else 1.0), int(bool(clamp01)),
+                               n, c, h, w, _lib.stream_ptr())
+    _lib.check(rc, "wmd_idwt_haar_f32")
+    return (out, disp) if disp_scale is not None else out
+
+
+def dwt_haar(x):
+    """x (N,C,H,W) even H,W -> ll (N,C,H/2,W/2), hf (N,C,3,H/2,W/2)."""
+    lib = _lib.load()
+    x = _dense(x)
+    n, c, h, w = x.shape
+    ll = torch.empty((n, c, h // 2, w // 2), dtype=_f32, device=x.device)
+    hf = torch.empty((n, c, 3, h // 2, w // 2), dtype=_f32, device=x.device)
+    rc = lib.wmd_dwt_haar_f32(_lib.ptr(x), _lib.ptr(ll), _lib.ptr(hf), n, c, h, w, _lib.stream_ptr())
+    _lib.check(rc, "wmd_dwt_haar_f32")
+    return ll, hf
+
+
+# --------------------------------------------------------------------------- masks
+def range_thresh(x, ratio, return_minmax=False):
+    """Per-sample (max - min) * ratio over everything but dim 0 -> (N,) fp32 on device."""
+    lib = _lib.load()
+    x = _dense(x)
+    n = x.shape[0]
+    per = x.numel() // max(n, 1)
+    thresh = torch.empty((n,), dtype=_f32, device=x.device)
+    mm = torch.empty((n, 2), dtype=_f32, device=x.device) if return_minmax else None
+    nbytes = lib.wmd_range_ws_bytes(n, per)
+    ws = _scratch.range(x.device, nbytes)
+    rc = lib.wmd_range_thresh_f32(_lib.ptr(x), n, per, float(ratio), _lib.ptr(thresh), _lib.ptr(mm),
+                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "wmd_range_thresh_f32")
+    return (thresh, mm) if return_minmax else thresh
+
+
+def level_masks(yh, thresh, n=None, h=None, w=None, device=None, want=("S0", "S1", "S2", "S3", "S4", "S5")):
+    """yh (N,3,H,W) or (N,1,3,H,W), thresh (N,) or None (all ones; then pass n,h,w,device).
+
+    Returns dict of uint8 (N,1,H,W) [S0-S2] / (N,1,2H,2W) [S3-S5] tensors."""
+    lib = _lib.load()
+    if thresh is not None:
+        yh = _dense(yh)
+        n, h, w = yh.shape[0], yh.shape[-2], yh.shape[-1]
+        device = yh.device
+        thresh = _dense(thresh)
+    out = {}
+    ptrs = []
+    for k in ("S0", "S1", "S2", "S3", "S4", "S5"):
+        if k in want:
+            hi = k in ("S3", "S4", "S5")
+            out[k] = torch.empty((n, 1, 2 * h if hi else h, 2 * w if hi else w), dtype=_u8, device=device)
+            ptrs.append(_lib.ptr(out[k]))
+        else:
+            ptrs.append(None)
+    rc = lib.wmd_level_masks(_lib.ptr(yh) if thresh is not None else None, _lib.ptr(thresh), *ptrs, n, h, w,
+                             _lib.stream_ptr())
+    _lib.check(rc, "wmd_level_masks")
+    return out
+
+
+def compact(mask, want_idxmap=True, want_pixels=True):
+    """mask uint8 (N,1,H,W) or (N,H,W) -> idxmap int32 (N,H,W) | None, pixels int32 (N*H*W,) | None, offsets int32 (N+1,)."""
+    lib = _lib.load()
+    mask = _dense(mask, _u8)
+    n, h, w = mask.shape[0], mask.shape[-2], mask.shape[-1]
+    dev = mask.device
+    idxmap = torch.empty((n, h, w), dtype=_i32, device=dev) if want_idxmap else None
+    pixels = torch.empty((n * h * w,), dtype=_i32, device=dev) if want_pixels else None
+    offsets = torch.empty((n + 1,), dtype=_i32, device=dev)
+    nbytes = lib.wmd_compact_ws_bytes(n, h, w)
+    ws = _scratch.compact(dev, nbytes)
+    rc = lib.wmd_compact_mask(_lib.ptr(mask), _lib.ptr(idxmap), _lib.ptr(pixels), _lib.ptr(offsets), n, h, w,
+                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "wmd_compact_mask")
+    return idxmap, pixels, offsets
+
+
+def gate_map(gate, idxmap=None):
+    """int32 map: gate ? (idxmap or linear index) : -1, shaped like gate without the channel dim."""
+    lib = _lib.load()
+    gate = _dense(gate, _u8)
+    out = torch.empty((gate.shape[0], gate.shape[-2], gate.shape[-1]), dtype=_i32, device=gate.device)
+    rc = lib.wmd_gate_map(_lib.ptr(gate), _lib.ptr(idxmap), _lib.ptr(out), gate.numel(), _lib.stream_ptr())
+    _lib.check(rc, "wmd_gate_map")
+    return out
+
+
+# --------------------------------------------------------------------------- layout
+def pad4(c):
+    return (int(c) + 3) // 4 * 4
+
+
+def nchw_to_rows(x, ld=None):
+    """(N,C,H,W) -> rows (N*H*W, ld) pixel-major.  Zero-copy when x is channels_last and C % 4 == 0."""
+    lib = _lib.load()
+    n, c, h, w = x.shape
+    ld = pad4(c) if ld is None else ld
+    if x.dtype == _f32 and ld == c and x.permute(0, 2, 3, 1).is_contiguous() and x.data_ptr() % 16 == 0:
+        return x.permute(0, 2, 3, 1).reshape(n * h * w, c)
+    x = _dense(x)
+    rows = torch.empty((n * h * w, ld), dtype=_f32, device=x.device)
+    rc = lib.wmd_nchw_to_rows_f32(_lib.ptr(x), _lib.ptr(rows), n, c, h * w, ld, _lib.stream_ptr())
+    _lib.check(rc, "wmd_nchw_to_rows_f32")
+    return rows
+
+
+def rows_to_nchw(rows, n, c, h, w):
+    lib = _lib.load()
+    rows = _dense(rows)
+    out = torch.empty((n, c, h, w), dtype=_f32, device=rows.device)
+    rc = lib.wmd_rows_to_nchw_f32(_lib.ptr(rows), _lib.ptr(out), n, c, h * w, rows.shape[1], _lib.stream_ptr())
+    _lib.check(rc, "wmd_rows_to_nchw_f32")
+    return out
+
+
+def gather_rows(x_nchw, pixels, count, max_rows=None, ld=None):
+    """rows[m] = x[n, :, y, x] at the listed pixels (pixels/count None = every pixel)."""
+    lib = _lib.load()
+    x = _dense(x_nchw)
+    n, c, h, w = x.shape
+    ld = pad4(c) if ld is None else ld
+    max_rows = n * h * w if max_rows is None else max_rows
+    rows = torch.zeros((max(max_rows, 1), ld), dtype=_f32, device=x.device)
+    rc = lib.wmd_gather_rows_nchw_f32(_lib.ptr(x), _lib.ptr(rows), ld, c, _lib.ptr(pixels), _lib.ptr(count),
+                                      max_rows, n, h, w, _lib.stream_ptr())
+    _lib.check(rc, "wmd_gather_rows_nchw_f32")
+    return rows
+
+
+def scatter_rows(rows, c, pixels, count, n, h, w, max_rows=None, out=None):
+    """Dense (N,C,H,W), zero except at the listed pixels where it takes rows[m, :c]."""
+    lib = _lib.load()
+    rows = _dense(rows)
+    if out is None:
+        out = torch.zeros((n, c, h, w), dtype=_f32, device=rows.device)
+    max_rows = min(rows.shape[0], n * h * w) if max_rows is None else max_rows
+    rc = lib.wmd_scatter_rows_nchw_f32(_lib.ptr(rows), rows.shape[1], c, _lib.ptr(pixels), _lib.ptr(count),
+                                       max_rows, _lib.ptr(out), n, h, w, _lib.stream_ptr())
+    _lib.check(rc, "wmd_scatter_rows_nchw_f32")
+    return out
+
+
+def pack_weight(weight):
+    """(Cout,Cin,k,k) -> packed (k*k*Cin, ldw) with ldw = pad4(Cout)."""
+    lib = _lib.load()
+    wt = _dense(weight.detach())
+    cout, cin = wt.shape[0], wt.shape[1]
+    taps = wt.shape[2] * wt.shape[3]
+    ldw = pad4(cout)
+    packed = torch.empty((taps * cin, ldw), dtype=_f32, device=wt.device)
+    rc = lib.wmd_pack_conv_weight_f32(_lib.ptr(wt), _lib.ptr(packed), cout, cin, taps, ldw, _lib.stream_ptr())
+    _lib.check(rc, "wmd_pack_conv_weight_f32")
+    return packed
+
+
+# --------------------------------------------------------------------------- conv
+def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act=ACT_NONE, act_param=0.0,
+              map0=None, shift0=0, x1=None, c1=0, gate=None, pixels=None, count=None, max_rows=None, out=None):
+    """Gather-GEMM convolution on pixel-major rows; see wmd_conv_rows_f32 in include/wmd.h.
+
+    x0: rows (R0, ld0); x1: optional dense rows (N*H*W, ld1); wpacked from pack_weight (taps*(c0+c1), ldw).
+    Returns y rows (max_rows, pad4(cout)).
+    """
+    lib = _lib.load()
+    dev = x0.device
+    total = n * h * w
+    max_rows = total if max_rows is None else int(max_rows)
+    ldy = pad4(cout)
+    if out is None:
+        out = torch.empty((max(max_rows, 1), ldy), dtype=_f32, device=dev)
+    assert wpacked.shape[0] == taps * (c0 + c1), (wpacked.shape, taps, c0, c1)
+    d = _lib.ConvDesc()
+    d.N, d.H, d.W = n, h, w
+    d.x0, d.c0, d.ld0 = _lib.ptr(x0, _f32), c0, x0.shape[1]
+    d.map0, d.shift0 = _lib.ptr(map0, _i32), shift0
+    d.x1, d.c1, d.ld1 = (_lib.ptr(x1, _f32), c1, x1.shape[1]) if x1 is not None else (None, 0, 0)
+    d.gate = _lib.ptr(gate, _u8)
+    d.w, d.bias = _lib.ptr(wpacked, _f32), _lib.ptr(bias, _f32)
+    d.cout, d.ldw, d.taps, d.pad_mode = cout, wpacked.shape[1], taps, pad
+    d.pixels, d.count, d.max_rows = _lib.ptr(pixels, _i32), _lib.ptr(count, _i32), max_rows
+    d.y, d.ldy = _lib.ptr(out, _f32), out.shape[1]
+    d.act, d.act_param = act, float(act_param)
+    rc = lib.wmd_conv_rows_f32(ctypes.byref(d), _lib.stream_ptr())
+    _lib.check(rc, "wmd_conv_rows_f32")
+    return out
+
+
+def head_conv3x3(t, c, off_a, wa, ba, n, h, w, cout, scale=1.0, act=ACT_NONE, pad=PAD_REFLECT, off_b=-1, wb=None,
+                 bb=None, idxmap=None, pixels=None, count=None, max_rows=None, out=None):
+    """3x3 stage of the coefficient heads -> dense (N,cout,H,W); see wmd_head_conv3x3_f32.
+
+    wa/wb: packed (9*c, cout) exactly (no padding: use pack_head_weight)."""
+    lib = _lib.load()
+    dev = t.device
+    total = n * h * w
+    max_rows = total if max_rows is None else int(max_rows)
+    if out is None:
+        out = (torch.zeros if pixels is not None else torch.empty)((n, cout, h, w), dtype=_f32, device=dev)
+    d = _lib.HeadDesc()
+    d.N, d.H, d.W = n, h, w
+    d.t, d.ld, d.c, d.off_a, d.off_b = _lib.ptr(t, _f32), t.shape[1], c, off_a, off_b
+    d.map = _lib.ptr(idxmap, _i32)
+    d.wa, d.ba, d.wb, d.bb = _lib.ptr(wa, _f32), _lib.ptr(ba, _f32), _lib.ptr(wb, _f32), _lib.ptr(bb, _f32)
+    d.cout, d.pad_mode, d.act, d.scale = cout, pad, act, float(scale)
+    d.pixels, d.count, d.max_rows = _lib.ptr(pixels, _i32), _lib.ptr(count, _i32), max_rows
+    d.out = _lib.ptr(out, _f32)
+    rc = lib.wmd_head_conv3x3_f32(ctypes.byref(d), _lib.stream_ptr())
+    _lib.check(rc, "wmd_head_conv3x3_f32")
+    return out
+
+
+def pack_head_weight(weight):
+    """(cout<=4, c, 3, 3) -> (9*c, cout) contiguous, the layout wmd_head_conv3x3_f32 stages in shared memory."""
+    lib = _lib.load()
+    wt = _dense(weight.detach())
+    cout, cin = wt.shape[0], wt.shape[1]
+    packed = torch.empty((9 * cin, cout), dtype=_f32, device=wt.device)
+    rc = lib.wmd_pack_conv_weight_f32(_lib.ptr(wt), _lib.ptr(packed), cout, cin, 9, cout, _lib.stream_ptr())
+    _lib.check(rc, "wmd_pack_conv_weight_f32")
+    return packed
