@@ -1,0 +1,272 @@
+"""GPU: decoder-level parity through the reference-facing API.
+
+ * against the golden vectors the unmodified reference produced (tests/golden, small configs),
+ * against the CPU oracle on the same seeded inputs, batched (oracle = per-sample reference semantics),
+ * at BASELINE.json's full sizes through size-independent properties (sparse(thr<0) == dense, known-answer
+   op counts, zero outside the wavelet mask, IDWT(DWT(x)) == x).
+Float bar: 1e-4 relative (north_star).  Masks / counts / total_ops: exact.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import kitti as okitti
+from oracle import nyu as onyu
+from wavelet_monodepth_b200 import kitti_decoders as kd
+from wavelet_monodepth_b200 import kitti_layers as kl
+from wavelet_monodepth_b200 import nyu_decoders as nd
+from wavelet_monodepth_b200 import ops, synth, wavelets
+
+from helpers import (REL_TOL, compare_outputs, golden_names, key_str, kitti_features, load_golden, nyu_features,
+                     rel_err, seeded_params)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _kitti(cls, meta):
+    mod = cls(np.array(meta["num_ch_enc"]))
+    sd = seeded_params(mod, meta)
+    mod.load_state_dict(sd, strict=False)
+    return mod.to(DEV).eval(), sd
+
+
+def _nyu(cls, meta):
+    mod = cls(enc_features=list(meta["enc_features"]), decoder_width=0.5)
+    sd = seeded_params(mod, meta)
+    mod.load_state_dict(sd, strict=False)
+    return mod.to(DEV).eval(), sd
+
+
+# ------------------------------------------------------------------------------------------ golden (reference outputs)
+def test_kitti_dense_vs_reference_golden():
+    want, meta = load_golden("kitti_tiny_dense")
+    mod, _ = _kitti(kd.DepthWaveProgressiveDecoder, meta)
+    with torch.no_grad():
+        got = mod(kitti_features(meta, DEV))
+    compare_outputs(got, want, "kitti dense native")
+
+
+@pytest.mark.parametrize("name", golden_names("kitti_tiny_sparse"))
+def test_kitti_sparse_vs_reference_golden(name):
+    want, meta = load_golden(name)
+    mod, _ = _kitti(kd.SparseDepthWaveProgressiveDecoder, meta)
+    got = mod(kitti_features(meta, DEV), meta["thresh_ratio"])
+    compare_outputs(got, want, name)
+
+
+def test_nyu_dense_vs_reference_golden():
+    want, meta = load_golden("nyu_tiny_dense")
+    mod, _ = _nyu(nd.DecoderWave, meta)
+    with torch.no_grad():
+        got = mod(nyu_features(meta, DEV))
+    compare_outputs(got, want, "nyu dense native")
+
+
+@pytest.mark.parametrize("name", golden_names("nyu_tiny_sparse"))
+def test_nyu_sparse_vs_reference_golden(name):
+    want, meta = load_golden(name)
+    mod, _ = _nyu(nd.SparseDecoderWave, meta)
+    got = mod(nyu_features(meta, DEV), meta["thresh_ratio"])
+    compare_outputs(got, want, name)
+
+
+# ------------------------------------------------------------------------------------------ batched vs per-sample oracle
+@pytest.mark.parametrize("thr", [0.2, 0.25, 0.42])
+def test_kitti_sparse_batched_equals_per_sample_oracle(thr):
+    _, meta = load_golden("kitti_tiny_dense")
+    mod, sd = _kitti(kd.SparseDepthWaveProgressiveDecoder, meta)
+    feats = kitti_features(meta)                       # N = 2
+    got = mod([f.to(DEV) for f in feats], thr)
+    per = [okitti.sparse_forward(sd, [f[b:b + 1] for f in feats], thr) for b in range(2)]
+    for k in per[0]:
+        if k == "total_ops" or (isinstance(k, tuple) and k[0] == "total_ops"):
+            assert got[k] == per[0][k] + per[1][k], k
+            continue
+        want = torch.cat([p[k] for p in per])
+        if "mask" in key_str(k):
+            assert torch.equal(got[k].cpu().bool(), want.bool()), k
+        else:
+            assert rel_err(got[k], want) <= REL_TOL, k
+    assert got["total_ops_per_sample"] == [p["total_ops"] for p in per]
+
+
+def test_nyu_sparse_batched_equals_per_sample_oracle():
+    _, meta = load_golden("nyu_tiny_dense")
+    mod, sd = _nyu(nd.SparseDecoderWave, meta)
+    feats = nyu_features(meta)
+    got = mod([f.to(DEV) for f in feats], 0.2)
+    per = [onyu.sparse_forward(sd, [f[b:b + 1] for f in feats], 0.2) for b in range(2)]
+    assert got["total_ops"] == per[0]["total_ops"] + per[1]["total_ops"]
+    for k in per[0]:
+        if k == "total_ops":
+            continue
+        want = torch.cat([p[k] for p in per])
+        if "mask" in key_str(k):
+            assert torch.equal(got[k].cpu().bool(), want.bool()), k
+        else:
+            assert rel_err(got[k], want) <= REL_TOL, k
+
+
+# ------------------------------------------------------------------------------------------ training path
+def test_dense_decoder_trains_through_native_idwt():
+    """KITTI/trainer.py:208-212: gradients flow through inverse_wt.  Compare grads with the CPU oracle graph."""
+    _, meta = load_golden("kitti_tiny_dense")
+    mod, sd = _kitti(kd.DepthWaveProgressiveDecoder, meta)
+    mod.train()
+    feats = kitti_features(meta)
+    out = mod([f.to(DEV) for f in feats])
+    loss = sum(out[("disp", s)].mean() for s in range(4))
+    loss.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    with torch.enable_grad():
+        o = okitti.dense_forward(params, feats)
+        sum(o[("disp", s)].mean() for s in range(4)).backward()
+    named = dict(mod.named_parameters())
+    checked = 0
+    for k, p in params.items():
+        if p.grad is None:
+            continue
+        g = named[k].grad
+        assert g is not None, k
+        assert rel_err(g, p.grad) <= 1e-3, k
+        checked += 1
+    assert checked >= 30
+    # and the native inference path agrees with the differentiable one
+    mod.eval()
+    with torch.no_grad():
+        nat = mod([f.to(DEV) for f in feats])
+    for s in range(4):
+        assert rel_err(nat[("disp", s)], out[("disp", s)].detach()) <= REL_TOL
+
+
+def test_weight_update_invalidates_packed_cache():
+    _, meta = load_golden("kitti_tiny_dense")
+    mod, _ = _kitti(kd.DepthWaveProgressiveDecoder, meta)
+    feats = kitti_features(meta, DEV)
+    with torch.no_grad():
+        a = mod(feats)[("disp", 0)].clone()
+        for p in mod.parameters():
+            p.mul_(1.05)
+        b = mod(feats)[("disp", 0)]
+    assert float((a - b).abs().max()) > 1e-4
+
+
+# ------------------------------------------------------------------------------------------ functional API (reference wire format)
+def test_functional_sparse_ops_vs_reference_golden():
+    want, meta = load_golden("sparse_ops")
+    cin, cout = meta["cin"], meta["cout"]
+    conv = kl.Conv3x3(cin, cout)
+    block = kl.ConvBlock(cin, cout, use_refl=True)
+    seq = nn.Sequential(kl.Conv1x1(cin, cin), nn.LeakyReLU(0.1, inplace=True), kl.Conv3x3(cin, 3))
+    for m in (conv, block, seq):
+        m.load_state_dict(synth.random_state_dict(synth.module_shapes(m), seed=meta["param_seed"]), strict=False)
+        m.to(DEV)
+    for a in ("dense", "half", "few", "empty"):
+        in_mask = torch.from_numpy(want["in_%s_mask" % a]).to(DEV)
+        xvals = torch.from_numpy(want["in_%s_xvals" % a]).to(DEV)
+        idxmap, n_ops = kl.mask2idxmap(in_mask)
+        assert n_ops == meta["h"] * meta["w"] and idxmap.dtype == torch.int64
+        for b in ("dense", "half", "few", "empty"):
+            out_mask = torch.from_numpy(want["in_%s_mask" % b]).to(DEV)
+            for pad in ("reflect", "constant", "replicate"):
+                flat, c, n_ops = kl.sparse_conv3x3(conv, xvals, idxmap, out_mask, padding=pad, make_result=False)
+                assert c == cout and n_ops == int(want["conv_%s_%s_%s_ops" % (a, b, pad)])
+                assert rel_err(flat, want["conv_%s_%s_%s" % (a, b, pad)]) <= REL_TOL, (a, b, pad)
+            dense, _ = kl.sparse_conv3x3(block, xvals, idxmap, out_mask)
+            assert rel_err(dense, want["block_%s_%s" % (a, b)]) <= REL_TOL
+            dense, n_ops = kl.sparse_conv3x3(seq, xvals, idxmap, out_mask, nonlin=torch.sigmoid)
+            assert n_ops == int(want["head_%s_%s_ops" % (a, b)])
+            assert rel_err(dense, want["head_%s_%s" % (a, b)]) <= REL_TOL
+            sel = kl.sparse_select(xvals, cin, idxmap, out_mask, pad=True)
+            assert torch.equal(sel.cpu(), torch.from_numpy(want["select_%s_%s" % (a, b)]))
+    lo_mask = torch.from_numpy(want["in_half_mask"]).to(DEV)
+    lo_idx, _ = kl.mask2idxmap(lo_mask)
+    vals, ochn = kl.sparse_upsample(torch.from_numpy(want["up_lo_vals"]).to(DEV), cin, lo_idx,
+                                    torch.from_numpy(want["up_skip"]).to(DEV),
+                                    torch.from_numpy(want["up_hi_mask"]).to(DEV), make_result=False)
+    assert ochn == cin + meta["cskip"] and torch.equal(vals.cpu(), torch.from_numpy(want["up_out"]))
+    yx = kl.mask2yx(lo_mask)
+    assert torch.equal(yx.cpu(), torch.nonzero(lo_mask[0, 0].cpu() > 0.5).t())
+
+
+def test_reference_module_runs_on_native_wavelets():
+    """sys.modules['pytorch_wavelets'] = wavelets is the documented drop-in: exercise that call convention."""
+    idwt = wavelets.IDWT(wave="haar", mode="zero").to(DEV)
+    yl = torch.rand(2, 1, 12, 40, device=DEV)
+    yh = torch.rand(2, 1, 3, 12, 40, device=DEV)
+    out = idwt((yl, list([yh])))
+    assert out.shape == (2, 1, 24, 80)
+    assert torch.equal(out, kd.SparseDepthWaveProgressiveDecoder.my_iwt_once((yl, [yh])))
+
+
+# ------------------------------------------------------------------------------------------ BASELINE sizes: properties
+def _full_kitti(ch, n, height, width, seed=1):
+    mod = kd.SparseDepthWaveProgressiveDecoder(np.array(ch))
+    synth.load_random(mod, seed=seed, gains={".2.conv.": 4.0})
+    dense = kd.DepthWaveProgressiveDecoder(np.array(ch))
+    dense.load_state_dict(mod.state_dict())
+    feats = [torch.rand(s, device=DEV, generator=torch.Generator(DEV).manual_seed(3 + i))
+             for i, s in enumerate(synth.kitti_feature_shapes(n, height, width, ch))]
+    return mod.to(DEV).eval(), dense.to(DEV).eval(), feats
+
+
+def test_full_size_r50_1024x320_known_answer_and_dense_equivalence():
+    mod, dense, feats = _full_kitti(synth.RESNET50_CH, 2, 320, 1024)
+    out = mod(feats, -1.0)
+    assert out["total_ops_per_sample"] == [17473692295, 17473692295]     # KITTI/sparsity_test_notebook.ipynb:1345
+    with torch.no_grad():
+        d = dense(feats)
+    for s in range(4):
+        assert out[("disp", s)].shape == (2, 1, 320 >> s, 1024 >> s)
+        assert rel_err(out[("disp", s)], d[("disp", s)]) <= REL_TOL
+        assert bool(out[("wavelet_mask", s)].all())
+
+
+def test_full_size_r18_640x192_bs16_sparse_properties():
+    mod, dense, feats = _full_kitti(synth.RESNET18_CH, 16, 192, 640)
+    out = mod(feats, 0.05)
+    with torch.no_grad():
+        d = dense(feats)
+    # level 4 is dense in both: identical coarsest outputs
+    assert rel_err(out[("disp", 3)], d[("disp", 3)]) <= REL_TOL
+    for s in (2, 1, 0):
+        m = out[("wavelet_mask", s)]
+        for band in ("LH", "HL", "HH"):
+            assert bool((out[("wavelets", s, band)][~m] == 0).all())
+        # nesting of the dilated sets
+        assert bool((out[("upconv1_mask", s)] | ~m).all()) and bool((out[("upsample_mask", s)] | ~out[("upconv1_mask", s)]).all())
+        assert bool((out[("upconv0_mask", s)] | ~out[("lowres_mask", s)]).all())
+    assert len(out["total_ops_per_sample"]) == 16 and out["total_ops"] == sum(out["total_ops_per_sample"])
+    # determinism: same inputs, same bits
+    out2 = mod(feats, 0.05)
+    assert torch.equal(out[("disp", 0)], out2[("disp", 0)])
+
+
+def test_full_size_nyu_densenet161_known_answer():
+    mod = nd.SparseDecoderWave(enc_features=list(synth.DENSENET161_CH), decoder_width=0.5)
+    synth.load_random(mod, seed=2)
+    mod = mod.to(DEV).eval()
+    dense = nd.DecoderWave(enc_features=list(synth.DENSENET161_CH), decoder_width=0.5)
+    dense.load_state_dict(mod.state_dict())
+    dense = dense.to(DEV).eval()
+    feats = [torch.rand(s, device=DEV) for s in synth.nyu_feature_shapes(1, 480, 640, synth.DENSENET161_CH)]
+    out = mod(feats, -10)
+    assert out["total_ops"] == 33463546800                                 # NYUv2/sparsity_test_notebook.ipynb:1344
+    with torch.no_grad():
+        d = dense(feats)
+    for s in range(4):
+        assert rel_err(out[("disp", s)], d[("disp", s)]) <= REL_TOL
+    assert out[("disp", 0)].shape == (1, 1, 240, 320)
+
+
+def test_full_size_haar_round_trip_1024x320_bs32():
+    x = torch.rand(32, 1, 320, 1024, device=DEV) * 80
+    ll, hf = ops.dwt_haar(x)
+    rec = ops.idwt_haar(ll, hf)
+    assert float((rec - x).abs().max()) <= 2e-5
+    # linearity: IDWT(a) + IDWT(b) == IDWT(a + b) up to rounding
+    ll2, hf2 = torch.rand_like(ll), torch.rand_like(hf)
+    lhs = ops.idwt_haar(ll + ll2, hf + hf2)
+    assert float((lhs - (rec + ops.idwt_haar(ll2, hf2))).abs().max()) <= 1e-4

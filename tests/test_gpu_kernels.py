@@ -1,0 +1,300 @@
+"""GPU: every libwmd kernel against the CPU oracle, through the C ABI (ops.* are thin ctypes wrappers).
+
+Bars: bit-exact for integer / byte / index work (masks, index maps, compaction, layout moves) and for the
+Haar synthesis (explicit roundings in the dependency's order); <= 1e-4 relative (north_star) for the
+floating-point convolutions, whose summation order differs from the CPU matmul.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import haar as ohaar
+from oracle import kitti as okitti
+from oracle import sparse_ops as osp
+from wavelet_monodepth_b200 import ops, wavelets
+from wavelet_monodepth_b200._lib import (ACT_ELU, ACT_LRELU, ACT_NONE, ACT_SIGMOID, PAD_REFLECT, PAD_REPLICATE,
+                                         PAD_ZERO)
+
+from helpers import REL_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, lo=-1.0, hi=1.0):
+    rs = np.random.RandomState(seed)
+    return torch.from_numpy(rs.uniform(lo, hi, size=shape).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------ Haar
+@pytest.mark.parametrize("shape", [(1, 1, 4, 6), (2, 1, 20, 64), (3, 2, 7, 5), (2, 1, 160, 512)])
+def test_idwt_bit_exact_vs_oracle(shape):
+    n, c, h, w = shape
+    ll, hf = rnd(n, c, h, w, seed=1, lo=0, hi=16), rnd(n, c, 3, h, w, seed=2, lo=-8, hi=8)
+    want = ohaar.DWTInverse("haar", "zero")((ll, [hf]))
+    got = ops.idwt_haar(ll.to(DEV), hf.to(DEV))
+    assert torch.equal(got.cpu(), want)
+    out, disp = ops.idwt_haar(ll.to(DEV), hf.to(DEV), disp_scale=0.25, clamp01=True)
+    assert torch.equal(out.cpu(), want)
+    assert torch.equal(disp.cpu(), torch.clamp(want / 4, 0, 1))
+    # the reference's own closed form (depth_decoder.py:225-239) agrees to rounding
+    assert float((got.cpu() - ohaar.closed_form_idwt(ll, hf)).abs().max()) < 4e-6
+
+
+def test_idwt_empty_batch_and_module_api():
+    idwt = wavelets.IDWT(wave="haar", mode="zero").to(DEV)
+    ll, hf = rnd(2, 1, 8, 10, seed=3).to(DEV), rnd(2, 1, 3, 8, 10, seed=4).to(DEV)
+    y = idwt((ll, [hf]))
+    assert y.shape == (2, 1, 16, 20)
+    assert ops.idwt_haar(ll[:0], hf[:0]).shape == (0, 1, 16, 20)
+    # non-contiguous band views (the decoders pass yh[:, :, k] style slices around)
+    big = rnd(2, 1, 3, 8, 20, seed=5).to(DEV)
+    y2 = idwt((ll, [big[..., ::2]]))
+    assert torch.equal(y2, idwt((ll, [big[..., ::2].contiguous()])))
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 240, 320), (1, 3, 6, 10)])
+def test_dwt_vs_oracle_and_perfect_reconstruction(shape):
+    x = rnd(*shape, seed=6, lo=0, hi=10)
+    j = 4 if shape[2] % 16 == 0 else 1
+    yl, yh = ohaar.DWTForward(J=j, wave="haar", mode="reflect")(x)
+    dwt = wavelets.DWT(J=j, wave="haar", mode="reflect").to(DEV)
+    gl, gh = dwt(x.to(DEV))
+    assert rel_err(gl, yl) < 1e-6
+    for a, b in zip(gh, yh):
+        assert a.shape == b.shape and float((a.cpu() - b).abs().max()) < 2e-6
+    rec = wavelets.IDWT(wave="haar").to(DEV)((gl, gh))
+    assert float((rec.cpu() - x).abs().max()) < 1e-5
+
+
+def test_idwt_autograd_matches_oracle():
+    ll = rnd(2, 1, 6, 8, seed=7).requires_grad_(True)
+    hf = rnd(2, 1, 3, 6, 8, seed=8).requires_grad_(True)
+    wgt = rnd(2, 1, 12, 16, seed=9)
+    (ohaar.DWTInverse("haar")((ll, [hf])) * wgt).sum().backward()
+    ll_g, hf_g = ll.detach().to(DEV).requires_grad_(True), hf.detach().to(DEV).requires_grad_(True)
+    (wavelets.IDWT("haar").to(DEV)((ll_g, [hf_g])) * wgt.to(DEV)).sum().backward()
+    assert float((ll_g.grad.cpu() - ll.grad).abs().max()) < 1e-6
+    assert float((hf_g.grad.cpu() - hf.grad).abs().max()) < 1e-6
+    x = rnd(1, 2, 8, 8, seed=10).requires_grad_(True)
+    yl, yh = ohaar.DWTForward(J=2, wave="haar")(x)
+    (yl.sum() + sum((h * h).sum() for h in yh)).backward()
+    xg = x.detach().to(DEV).requires_grad_(True)
+    gl, gh = wavelets.DWT(J=2, wave="haar").to(DEV)(xg)
+    (gl.sum() + sum((h * h).sum() for h in gh)).backward()
+    assert float((xg.grad.cpu() - x.grad).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ masks
+@pytest.mark.parametrize("n,per", [(1, 7), (3, 4096), (2, 320 * 1024), (5, 40 * 128 + 3)])
+def test_range_thresh_bit_exact(n, per):
+    x = rnd(n, per, seed=11, lo=-3, hi=9)
+    for ratio in (0.05, -1.0, 0.0):
+        want = torch.stack([(x[i].max() - x[i].min()) * ratio for i in range(n)])
+        got, mm = ops.range_thresh(x.to(DEV), ratio, return_minmax=True)
+        assert torch.equal(got.cpu(), want)
+        assert torch.equal(mm.cpu()[:, 0], x.min(1)[0]) and torch.equal(mm.cpu()[:, 1], x.max(1)[0])
+    # scratch is left clean: a second pass over different data is still right
+    y = rnd(n, per, seed=12)
+    assert torch.equal(ops.range_thresh(y.to(DEV), 0.1).cpu(), torch.stack([(y[i].max() - y[i].min()) * 0.1
+                                                                          for i in range(n)]))
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 5, 7), (2, 40, 128), (3, 33, 65), (1, 1, 1), (2, 64, 32)])
+def test_level_masks_bit_exact(n, h, w):
+    yh = rnd(n, 1, 3, h, w, seed=13)
+    yh[yh.abs() < 0.3] = 0                              # exact zeros: ratio 0 must drop them (strict >)
+    yl = rnd(n, 1, 2 * h, 2 * w, seed=14, lo=0, hi=4)
+    for ratio in (0.2, 0.0, -1.0, 0.5):
+        thresh = ops.range_thresh(yl.to(DEV), ratio)
+        got = ops.level_masks(yh.to(DEV), thresh)
+        for b in range(n):
+            want = okitti.level_masks(yl[b:b + 1], yh[b:b + 1], ratio)
+            for k in ("S0", "S1", "S2", "S3", "S4", "S5"):
+                assert torch.equal(got[k][b:b + 1].cpu().bool(), want[k].bool()), (ratio, b, k)
+    ones = ops.level_masks(None, None, n=n, h=h, w=w, device=torch.device(DEV))
+    assert all(bool(v.all()) for v in ones.values())
+
+
+@pytest.mark.parametrize("n,h,w,p", [(1, 10, 14, 0.5), (3, 40, 128, 0.2), (2, 31, 67, 0.9), (2, 8, 8, 0.0),
+                                     (4, 160, 512, 0.1), (1, 3, 5, 1.0)])
+def test_compaction_bit_exact(n, h, w, p):
+    rs = np.random.RandomState(15)
+    mask = torch.from_numpy((rs.uniform(size=(n, 1, h, w)) < p).astype(np.uint8))
+    idxmap, pixels, offsets = ops.compact(mask.to(DEV))
+    flat = mask.reshape(-1).bool()
+    want_idx = torch.where(flat, torch.cumsum(flat.long(), 0) - 1, torch.full((flat.numel(),), -1)).to(torch.int32)
+    assert torch.equal(idxmap.reshape(-1).cpu(), want_idx)
+    m = int(flat.sum())
+    assert torch.equal(pixels[:m].cpu().long(), torch.nonzero(flat).reshape(-1))
+    per = mask.reshape(n, -1).sum(1).long()
+    assert torch.equal(offsets.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(per, 0)]))
+    # batch-1 agrees with the reference's mask2idxmap (oracle restatement)
+    oi, _ = osp.index_map(mask[:1].float())
+    assert torch.equal(idxmap[0].cpu().long(), oi[0, 0])
+    gm = ops.gate_map(mask.to(DEV), idxmap)
+    assert torch.equal(gm.cpu(), idxmap.cpu())
+    lin = ops.gate_map(mask.to(DEV))
+    assert torch.equal(lin.reshape(-1).cpu().long(), torch.where(flat, torch.arange(flat.numel()), torch.tensor(-1)))
+
+
+# ------------------------------------------------------------------------------------------ layout
+@pytest.mark.parametrize("n,c,h,w", [(2, 64, 6, 20), (1, 3, 5, 7), (2, 138, 9, 4), (1, 2208, 15, 20)])
+def test_layout_round_trips(n, c, h, w):
+    x = rnd(n, c, h, w, seed=16)
+    rows = ops.nchw_to_rows(x.to(DEV))
+    ld = rows.shape[1]
+    assert ld == (c + 3) // 4 * 4
+    want = x.permute(0, 2, 3, 1).reshape(n * h * w, c)
+    assert torch.equal(rows[:, :c].cpu(), want)
+    assert ld == c or bool((rows[:, c:] == 0).all())
+    assert torch.equal(ops.rows_to_nchw(rows, n, c, h, w).cpu(), x)
+    if c % 4 == 0:   # channels_last input is used in place
+        cl = x.to(DEV).contiguous(memory_format=torch.channels_last)
+        r2 = ops.nchw_to_rows(cl)
+        assert r2.data_ptr() == cl.data_ptr() and torch.equal(r2.cpu(), want)
+    rs = np.random.RandomState(17)
+    mask = torch.from_numpy((rs.uniform(size=(n, 1, h, w)) < 0.4).astype(np.uint8)).to(DEV)
+    _, pixels, offsets = ops.compact(mask, want_idxmap=False)
+    m = int(offsets[n])
+    g = ops.gather_rows(x.to(DEV), pixels, offsets[n:])
+    assert torch.equal(g[:m, :c].cpu(), want[mask.reshape(-1).bool().cpu()])
+    dense = ops.scatter_rows(g, c, pixels, offsets[n:], n, h, w)
+    assert torch.equal(dense.cpu(), x * mask.cpu().float())
+
+
+def test_pack_weight_layout():
+    wt = rnd(5, 6, 3, 3, seed=18)
+    p = ops.pack_weight(wt.to(DEV)).cpu()
+    assert p.shape == (54, 8)
+    want = wt.permute(2, 3, 1, 0).reshape(54, 5)
+    assert torch.equal(p[:, :5], want) and bool((p[:, 5:] == 0).all())
+    ph = ops.pack_head_weight(wt[:3].to(DEV)).cpu()
+    assert torch.equal(ph, wt[:3].permute(2, 3, 1, 0).reshape(54, 3))
+
+
+# ------------------------------------------------------------------------------------------ conv
+def _torch_conv(x, wt, b, pad, act):
+    mode = {PAD_REFLECT: "reflect", PAD_REPLICATE: "replicate", PAD_ZERO: "constant"}[pad]
+    y = F.conv2d(F.pad(x, (1, 1, 1, 1), mode=mode), wt, b)
+    return {ACT_NONE: lambda t: t, ACT_ELU: F.elu, ACT_LRELU: lambda t: F.leaky_relu(t, 0.2),
+            ACT_SIGMOID: torch.sigmoid}[act](y)
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,pad,act", [
+    (2, 64, 32, 12, 20, PAD_REFLECT, ACT_ELU),          # thin tile config
+    (1, 96, 64, 9, 11, PAD_ZERO, ACT_LRELU),            # mid
+    (2, 40, 128, 6, 10, PAD_REPLICATE, ACT_NONE),       # wide, channel tail (40 % 32 != 0)
+    (1, 372, 138, 5, 7, PAD_REFLECT, ACT_LRELU),        # NYU up3 shapes: cout % 4 != 0
+    (1, 6, 5, 10, 14, PAD_REFLECT, ACT_SIGMOID),        # tiny, cin % 4 != 0
+    (3, 256, 256, 4, 6, PAD_REFLECT, ACT_ELU),
+])
+def test_dense_conv_rows_vs_torch(n, cin, cout, h, w, pad, act):
+    x, wt, b = rnd(n, cin, h, w, seed=19), rnd(cout, cin, 3, 3, seed=20, lo=-0.1, hi=0.1), rnd(cout, seed=21)
+    want = _torch_conv(x, wt, b, pad, act)
+    y = ops.conv_rows(ops.nchw_to_rows(x.to(DEV)), cin, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, n, h, w,
+                      pad=pad, act=act, act_param=0.2)
+    got = ops.rows_to_nchw(y, n, cout, h, w)
+    assert rel_err(got, want) <= REL_TOL
+
+
+def test_conv1x1_rows_vs_torch():
+    n, cin, cout, h, w = 2, 32, 64, 7, 9
+    x, wt, b = rnd(n, cin, h, w, seed=22), rnd(cout, cin, 1, 1, seed=23), rnd(cout, seed=24)
+    want = F.leaky_relu(F.conv2d(x, wt, b), 0.1)
+    y = ops.conv_rows(ops.nchw_to_rows(x.to(DEV)), cin, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, n, h, w,
+                      taps=1, act=ACT_LRELU, act_param=0.1)
+    assert rel_err(ops.rows_to_nchw(y, n, cout, h, w), want) <= REL_TOL
+
+
+def test_upsample_skip_fused_conv_vs_torch():
+    n, c0, c1, cout, h, w = 2, 16, 8, 32, 5, 6       # output grid 2h x 2w
+    lo, skip = rnd(n, c0, h, w, seed=25), rnd(n, c1, 2 * h, 2 * w, seed=26)
+    wt, b = rnd(cout, c0 + c1, 3, 3, seed=27, lo=-0.2, hi=0.2), rnd(cout, seed=28)
+    want = F.elu(F.conv2d(F.pad(torch.cat([F.interpolate(lo, scale_factor=2, mode="nearest"), skip], 1),
+                                (1, 1, 1, 1), mode="reflect"), wt, b))
+    y = ops.conv_rows(ops.nchw_to_rows(lo.to(DEV)), c0, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, n, 2 * h,
+                      2 * w, pad=PAD_REFLECT, act=ACT_ELU, shift0=1, x1=ops.nchw_to_rows(skip.to(DEV)), c1=c1)
+    assert rel_err(ops.rows_to_nchw(y, n, cout, 2 * h, 2 * w), want) <= REL_TOL
+
+
+def _sparse_case(seed, h, w, p_in, p_out):
+    rs = np.random.RandomState(seed)
+    in_mask = torch.from_numpy((rs.uniform(size=(1, 1, h, w)) < p_in).astype(np.float32))
+    out_mask = torch.from_numpy((rs.uniform(size=(1, 1, h, w)) < p_out).astype(np.float32))
+    return in_mask, out_mask
+
+
+@pytest.mark.parametrize("pad_name,pad", [("reflect", PAD_REFLECT), ("constant", PAD_ZERO), ("replicate", PAD_REPLICATE)])
+@pytest.mark.parametrize("p_in,p_out", [(0.6, 0.5), (0.1, 0.9), (1.0, 1.0), (0.5, 0.0), (0.0, 0.5)])
+def test_sparse_conv_vs_oracle(pad_name, pad, p_in, p_out):
+    """Per-sample oracle (batch-1 reference semantics) vs one batched launch over 2 samples."""
+    cin, cout, h, w = 24, 40, 13, 17
+    wt, b = rnd(cout, cin, 3, 3, seed=29, lo=-0.2, hi=0.2), rnd(cout, seed=30)
+    masks = [_sparse_case(31 + k, h, w, p_in, p_out) for k in range(2)]
+    xs = [rnd(cin * int(m[0].sum()), seed=40 + k) for k, m in enumerate(masks)]
+    wants = []
+    for (im, om), xv in zip(masks, xs):
+        idx, _ = osp.index_map(im)
+        dense, _ = osp.conv3x3(wt, b, xv, idx, om, nonlin=F.elu, padding=pad_name, make_result=True)
+        wants.append(dense)
+    in_mask = torch.cat([m[0] for m in masks]).to(torch.uint8).to(DEV)
+    out_mask = torch.cat([m[1] for m in masks]).to(torch.uint8).to(DEV)
+    rows = torch.cat([xv.reshape(cin, -1).t() for xv in xs] + [torch.zeros(1, cin)]).contiguous().to(DEV)
+    idxmap, _, _ = ops.compact(in_mask, want_pixels=False)
+    _, pixels, offsets = ops.compact(out_mask, want_idxmap=False)
+    y = ops.conv_rows(rows, cin, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, 2, h, w, pad=pad, act=ACT_ELU,
+                      map0=idxmap, pixels=pixels, count=offsets[2:])
+    got = ops.scatter_rows(y, cout, pixels, offsets[2:], 2, h, w)
+    assert rel_err(got, torch.cat(wants)) <= REL_TOL
+    assert bool((got.cpu()[out_mask.cpu().expand(-1, cout, -1, -1) == 0] == 0).all())
+
+
+def test_sparse_upsample_concat_gate_vs_oracle():
+    """The fused sparse_upsample + sparse_conv3x3 chain of one decoder level (depth_decoder.py:355-357)."""
+    c0, cs, cout, h, w = 16, 8, 32, 9, 11
+    rs = np.random.RandomState(50)
+    s0 = torch.from_numpy((rs.uniform(size=(1, 1, h, w)) < 0.25).astype(np.float32))
+    u = F.interpolate(s0, scale_factor=2, mode="nearest")
+    s2, s3, s4 = F.max_pool2d(s0, 5, 1, 2), F.max_pool2d(u, 5, 1, 2), F.max_pool2d(u, 3, 1, 1)
+    m2 = int(s2.sum())
+    xv = rnd(c0 * m2, seed=51)
+    skip = rnd(1, cs, 2 * h, 2 * w, seed=52)
+    wt, b = rnd(cout, c0 + cs, 3, 3, seed=53, lo=-0.2, hi=0.2), rnd(cout, seed=54)
+    map2, _ = osp.index_map(s2)
+    map3, _ = osp.index_map(s3)
+    up, uc = osp.upsample_concat(xv, c0, map2, skip, s3, make_result=False)
+    want, _ = osp.conv3x3(wt, b, up, map3, s4, nonlin=F.elu, padding="reflect", make_result=True)
+
+    rows = torch.cat([xv.reshape(c0, -1).t(), torch.zeros(1, c0)]).contiguous().to(DEV)
+    idx2, _, _ = ops.compact(s2.to(torch.uint8).to(DEV), want_pixels=False)
+    _, pix4, off4 = ops.compact(s4.to(torch.uint8).to(DEV), want_idxmap=False)
+    y = ops.conv_rows(rows, c0, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, 1, 2 * h, 2 * w, pad=PAD_REFLECT,
+                      act=ACT_ELU, map0=idx2, shift0=1, x1=ops.nchw_to_rows(skip.to(DEV)), c1=cs,
+                      gate=s3.to(torch.uint8).to(DEV), pixels=pix4, count=off4[1:])
+    got = ops.scatter_rows(y, cout, pix4, off4[1:], 1, 2 * h, 2 * w)
+    assert rel_err(got, want) <= REL_TOL
+
+
+@pytest.mark.parametrize("c,cout,dual", [(32, 3, True), (64, 1, False), (138, 3, False), (256, 3, True)])
+def test_head_conv_vs_oracle(c, cout, dual):
+    n, h, w = 2, 10, 12
+    t = rnd(n, 2 * c, h, w, seed=55)
+    wa, ba = rnd(cout, c, 3, 3, seed=56, lo=-0.3, hi=0.3), rnd(cout, seed=57)
+    wb, bb = rnd(cout, c, 3, 3, seed=58, lo=-0.3, hi=0.3), rnd(cout, seed=59)
+    a = torch.sigmoid(F.conv2d(F.pad(t[:, :c], (1, 1, 1, 1), mode="reflect"), wa, ba))
+    want = 4.0 * (a - torch.sigmoid(F.conv2d(F.pad(t[:, c:], (1, 1, 1, 1), mode="reflect"), wb, bb))) if dual else 4.0 * a
+    rows = ops.nchw_to_rows(t.to(DEV))
+    kw = dict(off_b=c, wb=ops.pack_head_weight(wb.to(DEV)), bb=bb.to(DEV)) if dual else {}
+    got = ops.head_conv3x3(rows, c, 0, ops.pack_head_weight(wa.to(DEV)), ba.to(DEV), n, h, w, cout, scale=4.0,
+                           act=ACT_SIGMOID, pad=PAD_REFLECT, **kw)
+    assert rel_err(got, want) <= REL_TOL
+    # sparse variant: outputs only at a pixel list, zero elsewhere (make_result semantics)
+    rs = np.random.RandomState(60)
+    mask = torch.from_numpy((rs.uniform(size=(n, 1, h, w)) < 0.3).astype(np.uint8)).to(DEV)
+    _, pix, off = ops.compact(mask, want_idxmap=False)
+    got_s = ops.head_conv3x3(rows, c, 0, ops.pack_head_weight(wa.to(DEV)), ba.to(DEV), n, h, w, cout, scale=4.0,
+                             act=ACT_SIGMOID, pad=PAD_REFLECT, pixels=pix, count=off[n:], **kw)
+    assert rel_err(got_s, want * mask.cpu().float()) <= REL_TOL
+    assert bool((got_s.cpu()[mask.cpu().expand(-1, cout, -1, -1) == 0] == 0).all())

@@ -46,6 +46,11 @@ class _PackCache:
         return ent[1]
 
 
+def _pm(fn):
+    """Active-row counts for the profiler's byte accounting; evaluated only while a profiler is installed."""
+    return fn() if ops._profiler is not None else None
+
+
 def _need_cuda(feats):
     for f in feats:
         if not f.is_cuda:
@@ -190,11 +195,12 @@ class _WaveDecoderBase(nn.Module):
                 _, pix5, off5 = ops.compact(masks["S5"], want_idxmap=False)
                 counts[i] = (off2, off4, off5)
                 xa = ops.conv_rows(x_rows, x_c, wp0, b0, c, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, map0=gmap,
-                                   pixels=pix2, count=off2[n:])
+                                   pixels=pix2, count=off2[n:], m_in0=_pm(lambda: (gmap >= 0).sum()))
                 xb = ops.conv_rows(xa, c, wp1, b1, c, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_ELU, map0=map2,
-                                   shift0=1, x1=skip_rows, c1=cs, gate=masks["S3"], pixels=pix4, count=off4[n:])
+                                   shift0=1, x1=skip_rows, c1=cs, gate=masks["S3"], pixels=pix4, count=off4[n:],
+                                   m_in0=off2[n:], m_in1=_pm(lambda: masks["S3"].sum()))
                 t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1,
-                                  pixels=pix4, count=off4[n:])
+                                  pixels=pix4, count=off4[n:], m_in0=off4[n:])
                 head_kw = dict(idxmap=map4, pixels=pix5, count=off5[n:])
                 prev_map = map4
             else:

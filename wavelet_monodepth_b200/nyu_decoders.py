@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from . import opcount, ops
 from ._lib import ACT_LRELU, ACT_NONE, PAD_REFLECT, PAD_REPLICATE, PAD_ZERO, WmdError
-from .kitti_decoders import _PackCache, _need_cuda
+from .kitti_decoders import _PackCache, _need_cuda, _pm
 from .kitti_layers import (make_result, mask2idxmap, mask2yx, sparse_conv3x3, sparse_select,  # noqa: F401
                            sparse_upsample)
 from .wavelets import IDWT
@@ -162,7 +162,8 @@ class _NyuWaveBase(nn.Module):
                 out[("wavelet_mask", 1 - s)] = masks["S5"].to(torch.float32)
                 xa = ops.conv_rows(x_rows, x_c, wp, b, cout, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_LRELU,
                                    act_param=0.2, map0=gmap, shift0=1, x1=ops.nchw_to_rows(skip), c1=cs,
-                                   gate=masks["S3"], pixels=pix4, count=off4[n:])
+                                   gate=masks["S3"], pixels=pix4, count=off4[n:],
+                                   m_in0=_pm(lambda: (gmap >= 0).sum()), m_in1=_pm(lambda: masks["S3"].sum()))
                 hcoef = ops.head_conv3x3(xa, cout, 0, wh, bh, n, 2 * h, 2 * w, 3, scale=scale, act=ACT_NONE,
                                          pad=PAD_ZERO, idxmap=map4, pixels=pix5, count=off5[n:])
                 prev_map = map4

@@ -52,6 +52,46 @@ class _Scratch:
 _scratch = _Scratch()
 
 
+class Profiler:
+    """Optional per-launch CUDA-event timing (bench.py's roofline pass).  Disabled unless installed."""
+
+    def __init__(self):
+        self.records = []          # (name, start_event, end_event, info dict)
+
+    def results(self):
+        """[(name, ms, info)] - call after a device synchronize."""
+        return [(n, s.elapsed_time(e), i) for n, s, e, i in self.records]
+
+
+_profiler = None
+
+
+def set_profiler(p):
+    global _profiler
+    _profiler = p
+
+
+class _prof:
+    """with _prof(name, info_fn): <one C-ABI call>  - brackets the call with events on the current stream."""
+    __slots__ = ("name", "info", "start")
+
+    def __init__(self, name, info=None):
+        self.name, self.info, self.start = name, info, None
+
+    def __enter__(self):
+        if _profiler is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.start is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _profiler.records.append((self.name, self.start, end, self.info() if self.info else {}))
+        return False
+
+
 # --------------------------------------------------------------------------- Haar
 def idwt_haar(ll, hf, disp_scale=None, clamp01=False):
     """ll (N,C,H,W), hf (N,C,3,H,W) -> out (N,C,2H,2W) [, disp = clamp?(out*disp_scale)]."""
@@ -62,9 +102,10 @@ def idwt_haar(ll, hf, disp_scale=None, clamp01=False):
         raise _lib.WmdError("idwt_haar: hf shape %s does not match ll %s" % (tuple(hf.shape), tuple(ll.shape)))
     out = torch.empty((n, c, 2 * h, 2 * w), dtype=_f32, device=ll.device)
     disp = torch.empty_like(out) if disp_scale is not None else None
-    rc = lib.wmd_idwt_haar_f32(_lib.ptr(ll), _lib.ptr(hf), _lib.ptr(out), _lib.ptr(disp),
-                               float(disp_scale if disp_scale is not None else 1.0), int(bool(clamp01)),
-                               n, c, h, w, _lib.stream_ptr())
+    with _prof('idwt_haar', lambda: dict(n=n, c=c, h=h, w=w, disp=disp is not None)):
+        rc = lib.wmd_idwt_haar_f32(_lib.ptr(ll), _lib.ptr(hf), _lib.ptr(out), _lib.ptr(disp),
+                                   float(disp_scale if disp_scale is not None else 1.0), int(bool(clamp01)),
+                                   n, c, h, w, _lib.stream_ptr())
     _lib.check(rc, "wmd_idwt_haar_f32")
     return (out, disp) if disp_scale is not None else out
 
@@ -76,7 +117,8 @@ def dwt_haar(x):
     n, c, h, w = x.shape
     ll = torch.empty((n, c, h // 2, w // 2), dtype=_f32, device=x.device)
     hf = torch.empty((n, c, 3, h // 2, w // 2), dtype=_f32, device=x.device)
-    rc = lib.wmd_dwt_haar_f32(_lib.ptr(x), _lib.ptr(ll), _lib.ptr(hf), n, c, h, w, _lib.stream_ptr())
+    with _prof('dwt_haar', lambda: dict(n=n, c=c, h=h, w=w)):
+        rc = lib.wmd_dwt_haar_f32(_lib.ptr(x), _lib.ptr(ll), _lib.ptr(hf), n, c, h, w, _lib.stream_ptr())
     _lib.check(rc, "wmd_dwt_haar_f32")
     return ll, hf
 
@@ -92,8 +134,9 @@ def range_thresh(x, ratio, return_minmax=False):
     mm = torch.empty((n, 2), dtype=_f32, device=x.device) if return_minmax else None
     nbytes = lib.wmd_range_ws_bytes(n, per)
     ws = _scratch.range(x.device, nbytes)
-    rc = lib.wmd_range_thresh_f32(_lib.ptr(x), n, per, float(ratio), _lib.ptr(thresh), _lib.ptr(mm),
-                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    with _prof('range_thresh', lambda: dict(n=n, per=per)):
+        rc = lib.wmd_range_thresh_f32(_lib.ptr(x), n, per, float(ratio), _lib.ptr(thresh), _lib.ptr(mm),
+                                      _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
     _lib.check(rc, "wmd_range_thresh_f32")
     return (thresh, mm) if return_minmax else thresh
 
@@ -117,8 +160,9 @@ def level_masks(yh, thresh, n=None, h=None, w=None, device=None, want=("S0", "S1
             ptrs.append(_lib.ptr(out[k]))
         else:
             ptrs.append(None)
-    rc = lib.wmd_level_masks(_lib.ptr(yh) if thresh is not None else None, _lib.ptr(thresh), *ptrs, n, h, w,
-                             _lib.stream_ptr())
+    with _prof('level_masks', lambda: dict(n=n, h=h, w=w, thresh=thresh is not None)):
+        rc = lib.wmd_level_masks(_lib.ptr(yh) if thresh is not None else None, _lib.ptr(thresh), *ptrs, n, h, w,
+                                 _lib.stream_ptr())
     _lib.check(rc, "wmd_level_masks")
     return out
 
@@ -134,8 +178,9 @@ def compact(mask, want_idxmap=True, want_pixels=True):
     offsets = torch.empty((n + 1,), dtype=_i32, device=dev)
     nbytes = lib.wmd_compact_ws_bytes(n, h, w)
     ws = _scratch.compact(dev, nbytes)
-    rc = lib.wmd_compact_mask(_lib.ptr(mask), _lib.ptr(idxmap), _lib.ptr(pixels), _lib.ptr(offsets), n, h, w,
-                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    with _prof('compact_mask', lambda: dict(n=n, h=h, w=w, idxmap=idxmap is not None, pixels=pixels is not None, offsets=offsets)):
+        rc = lib.wmd_compact_mask(_lib.ptr(mask), _lib.ptr(idxmap), _lib.ptr(pixels), _lib.ptr(offsets), n, h, w,
+                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
     _lib.check(rc, "wmd_compact_mask")
     return idxmap, pixels, offsets
 
@@ -145,7 +190,8 @@ def gate_map(gate, idxmap=None):
     lib = _lib.load()
     gate = _dense(gate, _u8)
     out = torch.empty((gate.shape[0], gate.shape[-2], gate.shape[-1]), dtype=_i32, device=gate.device)
-    rc = lib.wmd_gate_map(_lib.ptr(gate), _lib.ptr(idxmap), _lib.ptr(out), gate.numel(), _lib.stream_ptr())
+    with _prof('gate_map', lambda: dict(count=gate.numel())):
+        rc = lib.wmd_gate_map(_lib.ptr(gate), _lib.ptr(idxmap), _lib.ptr(out), gate.numel(), _lib.stream_ptr())
     _lib.check(rc, "wmd_gate_map")
     return out
 
@@ -164,7 +210,8 @@ def nchw_to_rows(x, ld=None):
         return x.permute(0, 2, 3, 1).reshape(n * h * w, c)
     x = _dense(x)
     rows = torch.empty((n * h * w, ld), dtype=_f32, device=x.device)
-    rc = lib.wmd_nchw_to_rows_f32(_lib.ptr(x), _lib.ptr(rows), n, c, h * w, ld, _lib.stream_ptr())
+    with _prof('nchw_to_rows', lambda: dict(n=n, c=c, hw=h * w, ld=ld)):
+        rc = lib.wmd_nchw_to_rows_f32(_lib.ptr(x), _lib.ptr(rows), n, c, h * w, ld, _lib.stream_ptr())
     _lib.check(rc, "wmd_nchw_to_rows_f32")
     return rows
 
@@ -173,7 +220,8 @@ def rows_to_nchw(rows, n, c, h, w):
     lib = _lib.load()
     rows = _dense(rows)
     out = torch.empty((n, c, h, w), dtype=_f32, device=rows.device)
-    rc = lib.wmd_rows_to_nchw_f32(_lib.ptr(rows), _lib.ptr(out), n, c, h * w, rows.shape[1], _lib.stream_ptr())
+    with _prof('rows_to_nchw', lambda: dict(n=n, c=c, hw=h * w)):
+        rc = lib.wmd_rows_to_nchw_f32(_lib.ptr(rows), _lib.ptr(out), n, c, h * w, rows.shape[1], _lib.stream_ptr())
     _lib.check(rc, "wmd_rows_to_nchw_f32")
     return out
 
@@ -220,8 +268,12 @@ def pack_weight(weight):
 
 # --------------------------------------------------------------------------- conv
 def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act=ACT_NONE, act_param=0.0,
-              map0=None, shift0=0, x1=None, c1=0, gate=None, pixels=None, count=None, max_rows=None, out=None):
+              map0=None, shift0=0, x1=None, c1=0, gate=None, pixels=None, count=None, max_rows=None, out=None,
+              m_in0=None, m_in1=None):
     """Gather-GEMM convolution on pixel-major rows; see wmd_conv_rows_f32 in include/wmd.h.
+
+    m_in0 / m_in1: optional active-row counts of the two sources (ints or 1-element device tensors), used only
+    by the profiler's algorithmic-byte accounting.
 
     x0: rows (R0, ld0); x1: optional dense rows (N*H*W, ld1); wpacked from pack_weight (taps*(c0+c1), ldw).
     Returns y rows (max_rows, pad4(cout)).
@@ -245,7 +297,8 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
     d.pixels, d.count, d.max_rows = _lib.ptr(pixels, _i32), _lib.ptr(count, _i32), max_rows
     d.y, d.ldy = _lib.ptr(out, _f32), out.shape[1]
     d.act, d.act_param = act, float(act_param)
-    rc = lib.wmd_conv_rows_f32(ctypes.byref(d), _lib.stream_ptr())
+    with _prof('conv_rows', lambda: dict(n=n, h=h, w=w, taps=taps, c0=c0, c1=c1, cout=cout, shift0=shift0, count=count, max_rows=max_rows, m_in0=m_in0, m_in1=m_in1)):
+        rc = lib.wmd_conv_rows_f32(ctypes.byref(d), _lib.stream_ptr())
     _lib.check(rc, "wmd_conv_rows_f32")
     return out
 
@@ -269,7 +322,8 @@ def head_conv3x3(t, c, off_a, wa, ba, n, h, w, cout, scale=1.0, act=ACT_NONE, pa
     d.cout, d.pad_mode, d.act, d.scale = cout, pad, act, float(scale)
     d.pixels, d.count, d.max_rows = _lib.ptr(pixels, _i32), _lib.ptr(count, _i32), max_rows
     d.out = _lib.ptr(out, _f32)
-    rc = lib.wmd_head_conv3x3_f32(ctypes.byref(d), _lib.stream_ptr())
+    with _prof('head_conv3x3', lambda: dict(n=n, h=h, w=w, c=c, cout=cout, dual=off_b >= 0, count=count, max_rows=max_rows)):
+        rc = lib.wmd_head_conv3x3_f32(ctypes.byref(d), _lib.stream_ptr())
     _lib.check(rc, "wmd_head_conv3x3_f32")
     return out
 

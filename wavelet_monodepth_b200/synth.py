@@ -25,11 +25,17 @@ RESNET50_CH = (64, 256, 512, 1024, 2048)
 DENSENET161_CH = (96, 96, 192, 384, 2208)
 
 
-def random_state_dict(shapes, seed, gains=None):
+def random_state_dict(shapes, seed, gains=None, highpass=None):
     """shapes: ordered {name: shape}; names ending in '.weight' / '.bias' are filled, others skipped.
 
     gains: optional {substring: factor}; every filled tensor whose name contains
     the substring is multiplied by factor (first match wins).
+    highpass: optional list of substrings; matching 3x3 weights get their spatial
+    mean removed per (out,in) pair and matching biases are zeroed, i.e. the conv
+    becomes a bank of zero-sum (edge / detail) filters.  Applied to the
+    coefficient heads this makes |yh| vanish on flat regions and peak at feature
+    discontinuities - the structure trained detail heads have (README.md:19-47)
+    and the only way random weights yield clustered, sparse threshold masks.
     """
     rs = np.random.RandomState(seed)
     out = OrderedDict()
@@ -42,6 +48,11 @@ def random_state_dict(shapes, seed, gains=None):
         elif not name.endswith(".bias"):
             continue
         arr = rs.uniform(-bound, bound, size=shape).astype(np.float32)
+        if highpass and any(sub in name for sub in highpass):
+            if arr.ndim == 4 and arr.shape[2] == 3:
+                arr = (arr - arr.mean(axis=(2, 3), keepdims=True)).astype(np.float32)
+            elif arr.ndim == 1:
+                arr = np.zeros_like(arr)
         if gains:
             for sub, g in gains.items():
                 if sub in name:
@@ -57,9 +68,9 @@ def module_shapes(module):
                        if k.endswith(".weight") or k.endswith(".bias"))
 
 
-def load_random(module, seed, gains=None):
+def load_random(module, seed, gains=None, highpass=None):
     """Fill ``module``'s conv parameters in place from ``random_state_dict``; returns the dict used."""
-    sd = random_state_dict(module_shapes(module), seed, gains)
+    sd = random_state_dict(module_shapes(module), seed, gains, highpass)
     missing = module.load_state_dict(sd, strict=False)
     assert not missing.unexpected_keys
     return sd
