@@ -207,49 +207,96 @@ def roofline_from(records, peak_gbs, peak_src, steps):
 _CPU_PARAMS = {}
 
 
-def cpu_frames_per_sec(wl_name, frames, warm=1):
-    """Times oracle.kitti.sparse_forward (the reference's batch-1 sparse path, restated) on the host cores."""
-    from oracle import kitti as okitti                     # allowed here: cpu_baseline / --impl reference legs only
+def _affinity_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _cpu_setup(wl_name):
     from wavelet_monodepth_b200.kitti_decoders import SparseDepthWaveProgressiveDecoder
     wl = WORKLOADS[wl_name]
-    torch.set_num_threads(os.cpu_count() or 1)
     if wl_name not in _CPU_PARAMS:
         _CPU_PARAMS[wl_name] = synth_params(SparseDepthWaveProgressiveDecoder(np.array(wl["ch"])))
-    sd = _CPU_PARAMS[wl_name]
-    times = []
+    return wl, _CPU_PARAMS[wl_name]
+
+
+def _cpu_frame(wl, sd, f):
+    from oracle import kitti as okitti                     # allowed here: cpu_baseline / --impl reference legs only
+    feats = synth_features(wl, 1, f % wl["per_gpu_batch"], pin=False)
+    t0 = time.perf_counter()
     with torch.no_grad():
-        for f in range(warm + frames):
-            feats = synth_features(wl, 1, f % wl["per_gpu_batch"], pin=False)
-            t0 = time.perf_counter()
-            okitti.sparse_forward(sd, feats, THRESH)
-            if f >= warm:
-                times.append(time.perf_counter() - t0)
-    return frames / sum(times), times
+        okitti.sparse_forward(sd, feats, THRESH)
+    return time.perf_counter() - t0
+
+
+def cpu_pick_threads(wl_name):
+    """The path is thousands of small ATen ops: more threads is not faster.  Probe a few intra-op thread counts up
+    to every core this process may use and keep the fastest (one frame each, after one warm-up)."""
+    if "threads" in _CPU_PARAMS:
+        return _CPU_PARAMS["threads"]
+    wl, sd = _cpu_setup(wl_name)
+    cores = _affinity_cores()
+    cands = sorted({c for c in (4, 8, 16, 32, cores) if c <= cores})
+    torch.set_num_threads(cands[0])
+    _cpu_frame(wl, sd, 0)
+    best, best_t = cands[0], None
+    for c in cands:
+        torch.set_num_threads(c)
+        t = _cpu_frame(wl, sd, 1)
+        log("[cpu arm] %d threads: %.3f s/frame" % (c, t))
+        if best_t is None or t < best_t:
+            best, best_t = c, t
+        if t > 4 * best_t:
+            break
+    torch.set_num_threads(best)
+    _CPU_PARAMS["threads"] = best
+    return best
+
+
+def cpu_frames_per_sec(wl_name, frames, budget_s=20.0, first_frame=0):
+    """Times oracle.kitti.sparse_forward (the reference's batch-1 sparse path, restated) on the host cores:
+    up to `frames` frames, stopping early once `budget_s` seconds of CPU work are spent."""
+    wl, sd = _cpu_setup(wl_name)
+    torch.set_num_threads(cpu_pick_threads(wl_name))
+    times = []
+    for f in range(frames):
+        times.append(_cpu_frame(wl, sd, first_frame + f))
+        if sum(times) >= budget_s:
+            break
+    return len(times) / sum(times), times
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload]
     frames_per_step = 4
-    for _ in range(args.warmup):
-        cpu_frames_per_sec(args.workload, 1, warm=0)
+    cores = cpu_pick_threads(args.workload)
+    per_step_budget = max(2.0, 150.0 / max(args.steps + args.warmup, 1))     # whole run stays within a few minutes
+    for w in range(args.warmup):
+        cpu_frames_per_sec(args.workload, 1, budget_s=per_step_budget, first_frame=w)
     t0 = time.perf_counter()
-    fps_steps = [cpu_frames_per_sec(args.workload, frames_per_step, warm=0)[0] for _ in range(args.steps)]
+    done, spent = 0, 0.0
+    for k in range(args.steps):
+        _, times = cpu_frames_per_sec(args.workload, frames_per_step, budget_s=per_step_budget,
+                                      first_frame=k * frames_per_step)
+        done += len(times)
+        spent += sum(times)
     wall = time.perf_counter() - t0
-    fps = frames_per_step * args.steps / sum(frames_per_step / f for f in fps_steps)
-    cores = torch.get_num_threads()
+    fps = done / spent
     line = {
         "impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * frames_per_step / fps, 2),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * spent / args.steps, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "thresh_ratio": THRESH, "frames_per_step": frames_per_step,
+        "config": {"workload": args.workload, "thresh_ratio": THRESH, "frames_per_step": round(done / args.steps, 2),
                    "note": "reference is Python/PyTorch and cannot travel to the GPU box; this arm times the oracle's "
                            "torch-CPU port of its batch-1 sparse decoder (pinned bit-exact against the reference, "
                            "oracle/pin_against_reference.py) on the host cores", "wall_s": round(wall, 1)},
         "cpu_baseline": {"value": round(fps, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d frames/step x %d steps of %s, one frame at a time (reference asserts batch 1)"
-                                   % (frames_per_step, args.steps, args.workload)},
+                         "sample": "%d frames in %d steps of %s, one frame at a time (reference asserts batch 1); "
+                                   "intra-op threads chosen by probe out of %d usable cores"
+                                   % (done, args.steps, args.workload, _affinity_cores())},
         "e2e": {"value": round(fps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -394,11 +441,11 @@ def run_native(args, rank, world, local_rank):
     # ---- 5. CPU baseline (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        frames = args.cpu_frames
-        fps, times = cpu_frames_per_sec(args.workload, frames)
+        fps, times = cpu_frames_per_sec(args.workload, args.cpu_frames, budget_s=20.0)
         cpu = {"value": round(fps, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "%d frames of %s (seeds of frames 0..%d), one at a time as the reference requires; %.1fs of CPU work"
-                         % (frames, args.workload, frames - 1, sum(times))}
+               "sample": "%d frames of %s (seeds of frames 0..%d), one at a time as the reference requires; %.1fs of "
+                         "CPU work; intra-op threads chosen by probe out of %d usable cores"
+                         % (len(times), args.workload, len(times) - 1, sum(times), _affinity_cores())}
 
     launches_t = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:

@@ -79,8 +79,9 @@ int wmd_dwt_haar_f32(const float* x, float* ll, float* hf, int N, int C, int H, 
  * thresh[n] = (max(x_n) - min(x_n)) * ratio over per_sample contiguous floats of sample n.
  * Replaces `thresh = (yl.max() - yl.min()) * thresh_ratio` (depth_decoder.py:308;
  * densedepth_decoder.py:316,363), per sample instead of the reference's batch-1.
- * minmax (2N floats: min,max) is optional.  ws: wmd_range_ws_bytes() bytes, must be
- * zero-filled before the FIRST use only (the kernel leaves it zeroed). */
+ * minmax (2N floats: min,max) is optional.  N <= 16384.  ws: wmd_range_ws_bytes() bytes whose first
+ * 64 KiB (per-sample ticket counters) must be zero before the FIRST use only: the kernel leaves them
+ * zeroed, for any later N, so one scratch buffer can be shared by all calls on a stream. */
 size_t wmd_range_ws_bytes(int N, long long per_sample);
 int wmd_range_thresh_f32(const float* x, int N, long long per_sample, float ratio, float* thresh, float* minmax,
                          void* ws, size_t ws_bytes, wmd_stream_t stream);

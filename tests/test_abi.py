@@ -33,7 +33,7 @@ def test_version_and_status_strings():
 
 def test_host_only_size_queries():
     lib = _lib.load()
-    assert lib.wmd_range_ws_bytes(4, 320 * 1024) >= 16 + 4 * 2 * 4
+    assert lib.wmd_range_ws_bytes(4, 320 * 1024) == 65536 + 4 * 64 * 2 * 4
     assert lib.wmd_compact_ws_bytes(32, 320, 1024) == ((32 * 320 * 1024 + 2047) // 2048) * 4
 
 

@@ -7,6 +7,10 @@ namespace wmd {
 // ------------------------------------------------------------------------------------ range -> threshold
 constexpr int kRangeThreads = 256;
 constexpr int kRangeMaxBlocks = 64;
+// The ticket counters live in a FIXED-size prefix of the workspace (independent of N), so the "left zeroed"
+// invariant survives calls with different batch sizes sharing one scratch buffer.
+constexpr int kRangeMaxN = 16384;
+constexpr size_t kRangeCounterBytes = static_cast<size_t>(kRangeMaxN) * sizeof(unsigned);
 
 static inline int range_blocks(long long per_sample) {
   long long b = (per_sample + 4095) / 4096;
@@ -276,21 +280,19 @@ __global__ void gate_map_kernel(const uint8_t* __restrict__ gate, const int32_t*
 
 // ---------------------------------------------------------------------------------------- C ABI
 extern "C" size_t wmd_range_ws_bytes(int N, long long per_sample) {
-  if (N <= 0) return 16;
-  const size_t counters = (static_cast<size_t>(N) * sizeof(unsigned) + 15) & ~static_cast<size_t>(15);
-  return counters + static_cast<size_t>(N) * wmd::range_blocks(per_sample) * 2 * sizeof(float);
+  if (N <= 0) return wmd::kRangeCounterBytes;
+  return wmd::kRangeCounterBytes + static_cast<size_t>(N) * wmd::range_blocks(per_sample) * 2 * sizeof(float);
 }
 
 extern "C" int wmd_range_thresh_f32(const float* x, int N, long long per_sample, float ratio, float* thresh,
                                     float* minmax, void* ws, size_t ws_bytes, wmd_stream_t stream) {
   using namespace wmd;
   WMD_REQUIRE(x && thresh && ws, WMD_ERR_ARG);
-  WMD_REQUIRE(N >= 0 && per_sample > 0, WMD_ERR_SHAPE);
+  WMD_REQUIRE(N >= 0 && N <= kRangeMaxN && per_sample > 0, WMD_ERR_SHAPE);
   if (N == 0) return WMD_OK;
   WMD_REQUIRE(ws_bytes >= wmd_range_ws_bytes(N, per_sample), WMD_ERR_WORKSPACE);
-  const size_t counters = (static_cast<size_t>(N) * sizeof(unsigned) + 15) & ~static_cast<size_t>(15);
   unsigned* cnt = static_cast<unsigned*>(ws);
-  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + counters);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + kRangeCounterBytes);
   dim3 grid(range_blocks(per_sample), N);
   range_thresh_kernel<<<grid, kRangeThreads, 0, as_stream(stream)>>>(x, per_sample, ratio, thresh, minmax, cnt, partial);
   return launched();

@@ -135,7 +135,9 @@ class _NyuWaveBase(nn.Module):
         wh, bh = self._head("wave1", self.wave1)
         hcoef = ops.head_conv3x3(d1, f // 2, 0, wh, bh, n, h, w, 3, scale=float(2 ** 2), act=ACT_NONE, pad=PAD_ZERO)
         if sparse:
-            out[("wavelet_mask", 2)] = torch.ones((n, 1, h, w), dtype=torch.float32, device=xb.device)
+            # the reference builds this one as ones_like(h[:, 0]) with h already (N,1,3,H,W): a 3-channel map
+            # (densedepth_decoder.py:301-303); kept as is
+            out[("wavelet_mask", 2)] = torch.ones((n, 3, h, w), dtype=torch.float32, device=xb.device)
         out[("wavelets", 2, "LL")] = ll
         for k, band in enumerate(("LH", "HL", "HH")):
             out[("wavelets", 2, band)] = hcoef[:, k:k + 1]

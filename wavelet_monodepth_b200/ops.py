@@ -102,6 +102,8 @@ def idwt_haar(ll, hf, disp_scale=None, clamp01=False):
         raise _lib.WmdError("idwt_haar: hf shape %s does not match ll %s" % (tuple(hf.shape), tuple(ll.shape)))
     out = torch.empty((n, c, 2 * h, 2 * w), dtype=_f32, device=ll.device)
     disp = torch.empty_like(out) if disp_scale is not None else None
+    if out.numel() == 0:
+        return (out, disp) if disp_scale is not None else out
     with _prof('idwt_haar', lambda: dict(n=n, c=c, h=h, w=w, disp=disp is not None)):
         rc = lib.wmd_idwt_haar_f32(_lib.ptr(ll), _lib.ptr(hf), _lib.ptr(out), _lib.ptr(disp),
                                    float(disp_scale if disp_scale is not None else 1.0), int(bool(clamp01)),
@@ -117,6 +119,8 @@ def dwt_haar(x):
     n, c, h, w = x.shape
     ll = torch.empty((n, c, h // 2, w // 2), dtype=_f32, device=x.device)
     hf = torch.empty((n, c, 3, h // 2, w // 2), dtype=_f32, device=x.device)
+    if x.numel() == 0:
+        return ll, hf
     with _prof('dwt_haar', lambda: dict(n=n, c=c, h=h, w=w)):
         rc = lib.wmd_dwt_haar_f32(_lib.ptr(x), _lib.ptr(ll), _lib.ptr(hf), n, c, h, w, _lib.stream_ptr())
     _lib.check(rc, "wmd_dwt_haar_f32")
