@@ -64,7 +64,7 @@ def test_dwt_vs_oracle_and_perfect_reconstruction(shape):
     gl, gh = dwt(x.to(DEV))
     assert rel_err(gl, yl) < 1e-6
     for a, b in zip(gh, yh):
-        assert a.shape == b.shape and rel_err(a, b) < 1e-6
+        assert a.shape == b.shape and rel_err(a, b) < 2e-6
     rec = wavelets.IDWT(wave="haar").to(DEV)((gl, gh))
     assert rel_err(rec, x) < 2e-6
 
