@@ -167,7 +167,7 @@ def test_layout_round_trips(n, c, h, w):
 
 def test_pack_weight_layout():
     wt = rnd(5, 6, 3, 3, seed=18)
-    p = ops.pack_weight(wt.to(DEV)).cpu()
+    p = ops.pack_weight(wt.to(DEV), kind="simt").data.cpu()
     assert p.shape == (54, 8)
     want = wt.permute(2, 3, 1, 0).reshape(54, 5)
     assert torch.equal(p[:, :5], want) and bool((p[:, 5:] == 0).all())
@@ -176,6 +176,12 @@ def test_pack_weight_layout():
 
 
 # ------------------------------------------------------------------------------------------ conv
+@pytest.fixture(params=["simt", "tc"])
+def kind(request):
+    """Both gather-GEMM engines answer to the same contract: fp32 FMA tiles and tcgen05 3xTF32."""
+    return request.param
+
+
 def _torch_conv(x, wt, b, pad, act):
     mode = {PAD_REFLECT: "reflect", PAD_REPLICATE: "replicate", PAD_ZERO: "constant"}[pad]
     y = F.conv2d(F.pad(x, (1, 1, 1, 1), mode=mode), wt, b)
@@ -191,31 +197,31 @@ def _torch_conv(x, wt, b, pad, act):
     (1, 6, 5, 10, 14, PAD_REFLECT, ACT_SIGMOID),        # tiny, cin % 4 != 0
     (3, 256, 256, 4, 6, PAD_REFLECT, ACT_ELU),
 ])
-def test_dense_conv_rows_vs_torch(n, cin, cout, h, w, pad, act):
+def test_dense_conv_rows_vs_torch(n, cin, cout, h, w, pad, act, kind):
     x, wt, b = rnd(n, cin, h, w, seed=19), rnd(cout, cin, 3, 3, seed=20, lo=-0.1, hi=0.1), rnd(cout, seed=21)
     want = _torch_conv(x, wt, b, pad, act)
-    y = ops.conv_rows(ops.nchw_to_rows(x.to(DEV)), cin, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, n, h, w,
+    y = ops.conv_rows(ops.nchw_to_rows(x.to(DEV)), cin, ops.pack_weight(wt.to(DEV), kind=kind), b.to(DEV), cout, n, h, w,
                       pad=pad, act=act, act_param=0.2)
     got = ops.rows_to_nchw(y, n, cout, h, w)
     assert rel_err(got, want) <= REL_TOL
 
 
-def test_conv1x1_rows_vs_torch():
+def test_conv1x1_rows_vs_torch(kind):
     n, cin, cout, h, w = 2, 32, 64, 7, 9
     x, wt, b = rnd(n, cin, h, w, seed=22), rnd(cout, cin, 1, 1, seed=23), rnd(cout, seed=24)
     want = F.leaky_relu(F.conv2d(x, wt, b), 0.1)
-    y = ops.conv_rows(ops.nchw_to_rows(x.to(DEV)), cin, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, n, h, w,
+    y = ops.conv_rows(ops.nchw_to_rows(x.to(DEV)), cin, ops.pack_weight(wt.to(DEV), kind=kind), b.to(DEV), cout, n, h, w,
                       taps=1, act=ACT_LRELU, act_param=0.1)
     assert rel_err(ops.rows_to_nchw(y, n, cout, h, w), want) <= REL_TOL
 
 
-def test_upsample_skip_fused_conv_vs_torch():
+def test_upsample_skip_fused_conv_vs_torch(kind):
     n, c0, c1, cout, h, w = 2, 16, 8, 32, 5, 6       # output grid 2h x 2w
     lo, skip = rnd(n, c0, h, w, seed=25), rnd(n, c1, 2 * h, 2 * w, seed=26)
     wt, b = rnd(cout, c0 + c1, 3, 3, seed=27, lo=-0.2, hi=0.2), rnd(cout, seed=28)
     want = F.elu(F.conv2d(F.pad(torch.cat([F.interpolate(lo, scale_factor=2, mode="nearest"), skip], 1),
                                 (1, 1, 1, 1), mode="reflect"), wt, b))
-    y = ops.conv_rows(ops.nchw_to_rows(lo.to(DEV)), c0, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, n, 2 * h,
+    y = ops.conv_rows(ops.nchw_to_rows(lo.to(DEV)), c0, ops.pack_weight(wt.to(DEV), c1, kind=kind), b.to(DEV), cout, n, 2 * h,
                       2 * w, pad=PAD_REFLECT, act=ACT_ELU, shift0=1, x1=ops.nchw_to_rows(skip.to(DEV)), c1=c1)
     assert rel_err(ops.rows_to_nchw(y, n, cout, 2 * h, 2 * w), want) <= REL_TOL
 
@@ -229,7 +235,7 @@ def _sparse_case(seed, h, w, p_in, p_out):
 
 @pytest.mark.parametrize("pad_name,pad", [("reflect", PAD_REFLECT), ("constant", PAD_ZERO), ("replicate", PAD_REPLICATE)])
 @pytest.mark.parametrize("p_in,p_out", [(0.6, 0.5), (0.1, 0.9), (1.0, 1.0), (0.5, 0.0), (0.0, 0.5)])
-def test_sparse_conv_vs_oracle(pad_name, pad, p_in, p_out):
+def test_sparse_conv_vs_oracle(pad_name, pad, p_in, p_out, kind):
     """Per-sample oracle (batch-1 reference semantics) vs one batched launch over 2 samples."""
     cin, cout, h, w = 24, 40, 13, 17
     wt, b = rnd(cout, cin, 3, 3, seed=29, lo=-0.2, hi=0.2), rnd(cout, seed=30)
@@ -245,14 +251,14 @@ def test_sparse_conv_vs_oracle(pad_name, pad, p_in, p_out):
     rows = torch.cat([xv.reshape(cin, -1).t() for xv in xs] + [torch.zeros(1, cin)]).contiguous().to(DEV)
     idxmap, _, _ = ops.compact(in_mask, want_pixels=False)
     _, pixels, offsets = ops.compact(out_mask, want_idxmap=False)
-    y = ops.conv_rows(rows, cin, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, 2, h, w, pad=pad, act=ACT_ELU,
+    y = ops.conv_rows(rows, cin, ops.pack_weight(wt.to(DEV), kind=kind), b.to(DEV), cout, 2, h, w, pad=pad, act=ACT_ELU,
                       map0=idxmap, pixels=pixels, count=offsets[2:])
     got = ops.scatter_rows(y, cout, pixels, offsets[2:], 2, h, w)
     assert rel_err(got, torch.cat(wants)) <= REL_TOL
     assert bool((got.cpu()[out_mask.cpu().expand(-1, cout, -1, -1) == 0] == 0).all())
 
 
-def test_sparse_upsample_concat_gate_vs_oracle():
+def test_sparse_upsample_concat_gate_vs_oracle(kind):
     """The fused sparse_upsample + sparse_conv3x3 chain of one decoder level (depth_decoder.py:355-357)."""
     c0, cs, cout, h, w = 16, 8, 32, 9, 11
     rs = np.random.RandomState(50)
@@ -271,7 +277,7 @@ def test_sparse_upsample_concat_gate_vs_oracle():
     rows = torch.cat([xv.reshape(c0, -1).t(), torch.zeros(1, c0)]).contiguous().to(DEV)
     idx2, _, _ = ops.compact(s2.to(torch.uint8).to(DEV), want_pixels=False)
     _, pix4, off4 = ops.compact(s4.to(torch.uint8).to(DEV), want_idxmap=False)
-    y = ops.conv_rows(rows, c0, ops.pack_weight(wt.to(DEV)), b.to(DEV), cout, 1, 2 * h, 2 * w, pad=PAD_REFLECT,
+    y = ops.conv_rows(rows, c0, ops.pack_weight(wt.to(DEV), cs, kind=kind), b.to(DEV), cout, 1, 2 * h, 2 * w, pad=PAD_REFLECT,
                       act=ACT_ELU, map0=idx2, shift0=1, x1=ops.nchw_to_rows(skip.to(DEV)), c1=cs,
                       gate=s3.to(torch.uint8).to(DEV), pixels=pix4, count=off4[1:])
     got = ops.scatter_rows(y, cout, pix4, off4[1:], 1, 2 * h, 2 * w)

@@ -15,7 +15,13 @@ from wavelet_monodepth_b200.nyu_decoders import DecoderWave
 
 from helpers import (compare_outputs, golden_names, kitti_features, load_golden, nyu_features, seeded_params)
 
-torch.set_grad_enabled(False)
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():
+        yield
+
+
 
 
 def test_kitti_dense_matches_reference_golden():

@@ -129,14 +129,17 @@ class _WaveDecoderBase(nn.Module):
     # ---- packed parameters ------------------------------------------------------------------
     def _upconv(self, i, j):
         conv = self.convs[("upconv", i, j)].conv.conv
-        return self._packs.get(("upconv", i, j), [conv.weight], lambda: ops.pack_weight(conv.weight)), conv.bias.detach()
+        c1 = int(self.num_ch_enc[i - 1]) if j == 1 else 0          # upconv(i,1) reads the skip map as gather source 1
+        kind = ops.default_conv_kind()
+        return self._packs.get(("upconv", i, j, kind), [conv.weight], lambda: ops.pack_weight(conv.weight, c1)), conv.bias.detach()
 
     def _head_1x1(self, i):
         """Concatenated 1x1 stages of the level's heads: [LL (i==4) | + | -] -> (packed (C, ld), bias, offsets)."""
         names = ([0] if i == 4 else []) + [1, -1]
         convs = [self.convs[("waveconv", i, j)][0].conv for j in names]
         wts = [c.weight for c in convs]
-        packed = self._packs.get(("head1x1", i), wts, lambda: ops.pack_weight(torch.cat([w.detach() for w in wts], 0)))
+        packed = self._packs.get(("head1x1", i, ops.default_conv_kind()), wts,
+                                 lambda: ops.pack_weight(torch.cat([w.detach() for w in wts], 0)))
         bias = self._packs.get(("head1x1b", i), [c.bias for c in convs],
                                lambda: torch.cat([c.bias.detach() for c in convs], 0).contiguous())
         offs, run = {}, 0

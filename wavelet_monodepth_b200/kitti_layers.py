@@ -158,10 +158,11 @@ def sparse_select(xvals, xchn, xidxmap, ymask, ufactor=1, pad=False):
 _eye_cache = {}
 
 
-def _identity_weight(c, device):
-    key = (c, str(device))
+def _identity_weight(c, device, c1=0):
+    # exact copies need the fp32 FMA engine (1.0 * x + 0 is exact; a tf32 split is not a copy)
+    key = (c, c1, str(device))
     if key not in _eye_cache:
-        _eye_cache[key] = ops.pack_weight(torch.eye(c, device=device).reshape(c, c, 1, 1))
+        _eye_cache[key] = ops.pack_weight(torch.eye(c, device=device).reshape(c, c, 1, 1), c1, kind="simt")
     return _eye_cache[key]
 
 
@@ -224,7 +225,7 @@ def sparse_upsample(xvals, xchn, xidxmap, skip, mask, make_result=True):
     rows, _ = _cm_to_rows(xvals, xchn)
     _, pixels, offsets = ops.compact(_mask_u8(mask), want_idxmap=False)
     # identity 1x1 over the concatenated (upsampled | skip) channels
-    eye = _identity_weight(ochn, rows.device)
+    eye = _identity_weight(ochn, rows.device, cs)
     out = ops.conv_rows(rows, xchn, eye, None, ochn, 1, oh, ow, taps=1, pad=PAD_ZERO, act=ACT_NONE,
                         map0=xidxmap.reshape(1, xh, xw).to(torch.int32).contiguous(), shift0=1,
                         x1=ops.nchw_to_rows(skip), c1=cs, pixels=pixels, count=offsets[1:])

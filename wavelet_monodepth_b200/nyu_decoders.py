@@ -102,9 +102,10 @@ class _NyuWaveBase(nn.Module):
         self._depthwise = bool(dw_waveconv or dw_upconv)
         self._packs = _PackCache()
 
-    def _gemm(self, name, layer):
+    def _gemm(self, name, layer, c1=0):
         conv = layer.conv
-        return self._packs.get(("gemm", name), [conv.weight], lambda: ops.pack_weight(conv.weight)), conv.bias.detach()
+        return self._packs.get(("gemm", name, ops.default_conv_kind()), [conv.weight],
+                               lambda: ops.pack_weight(conv.weight, c1)), conv.bias.detach()
 
     def _head(self, name, layer):
         conv = layer.conv
@@ -123,8 +124,8 @@ class _NyuWaveBase(nn.Module):
         counts = []
         wp, b = self._gemm("conv2", self.conv2)
         d0 = ops.conv_rows(ops.nchw_to_rows(xb), xb.shape[1], wp, b, f, n, h, w, pad=PAD_REPLICATE, act=ACT_NONE)
-        wp, b = self._gemm("up1", self.up1.convA)
         skip = blocks[-2]
+        wp, b = self._gemm("up1", self.up1.convA, skip.shape[1])
         d1 = ops.conv_rows(d0, f, wp, b, f // 2, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_LRELU, act_param=0.2,
                            shift0=1, x1=ops.nchw_to_rows(skip), c1=skip.shape[1])
         h, w = 2 * h, 2 * w
@@ -150,7 +151,7 @@ class _NyuWaveBase(nn.Module):
             skip = blocks[-3 - s]
             cs = skip.shape[1]
             cout = up.convA.conv.weight.shape[0]
-            wp, b = self._gemm(name, up.convA)
+            wp, b = self._gemm(name, up.convA, cs)
             wh, bh = self._head("wave%d" % (s + 2), wave)
             if tuple(skip.shape[2:]) != (2 * h, 2 * w):
                 raise WmdError("skip block has shape %s, expected spatial %s" % (tuple(skip.shape), (2 * h, 2 * w)))

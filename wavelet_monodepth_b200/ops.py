@@ -257,17 +257,50 @@ def scatter_rows(rows, c, pixels, count, n, h, w, max_rows=None, out=None):
     return out
 
 
-def pack_weight(weight):
-    """(Cout,Cin,k,k) -> packed (k*k*Cin, ldw) with ldw = pad4(Cout)."""
+class PackedW:
+    """A conv weight packed for one of the two gather-GEMM engines ('simt' fp32 FMA, 'tc' tcgen05 3xTF32)."""
+    __slots__ = ("data", "kind", "taps", "c0", "c1", "cout")
+
+    def __init__(self, data, kind, taps, c0, c1, cout):
+        self.data, self.kind, self.taps, self.c0, self.c1, self.cout = data, kind, taps, c0, c1, cout
+
+
+TC_MIN_COUT = 128     # the tcgen05 tile is 256 x 128: narrower outputs waste the tensor pipe, the FMA tiles win
+
+
+def default_conv_kind():
+    """Engine used when a caller does not ask for one: env WMD_CONV_IMPL = auto | simt | tc.
+
+    auto (default): tcgen05 3xTF32 for cout >= 128 (the layers that carry ~85 % of the decoder's FLOPs),
+    fp32 FMA tiles below."""
+    import os
+    return os.environ.get("WMD_CONV_IMPL", "auto")
+
+
+def pack_weight(weight, c1=0, kind=None):
+    """(Cout,Cin,k,k) conv weight -> PackedW.  c1 = trailing input channels that come from gather source 1.
+
+    simt: [k*k][Cin][ldw] rows (ldw = pad4(Cout)).  tc: per (n-tile, 32-channel chunk) swizzled smem images
+    [tf32 hi | tf32 lo] (chunk boundaries follow the two gather sources, hence c1 matters)."""
     lib = _lib.load()
+    kind = kind or default_conv_kind()
     wt = _dense(weight.detach())
     cout, cin = wt.shape[0], wt.shape[1]
     taps = wt.shape[2] * wt.shape[3]
+    c0 = cin - c1
+    if kind == "auto":
+        kind = "tc" if cout >= TC_MIN_COUT else "simt"
+    if kind == "tc":
+        nfl = lib.wmd_conv_tc_weight_floats(cout, c0, c1, taps)
+        packed = torch.empty((nfl,), dtype=_f32, device=wt.device)
+        rc = lib.wmd_pack_conv_weight_tc_f32(_lib.ptr(wt), _lib.ptr(packed), cout, c0, c1, taps, _lib.stream_ptr())
+        _lib.check(rc, "wmd_pack_conv_weight_tc_f32")
+        return PackedW(packed, "tc", taps, c0, c1, cout)
     ldw = pad4(cout)
     packed = torch.empty((taps * cin, ldw), dtype=_f32, device=wt.device)
     rc = lib.wmd_pack_conv_weight_f32(_lib.ptr(wt), _lib.ptr(packed), cout, cin, taps, ldw, _lib.stream_ptr())
     _lib.check(rc, "wmd_pack_conv_weight_f32")
-    return packed
+    return PackedW(packed, "simt", taps, c0, c1, cout)
 
 
 # --------------------------------------------------------------------------- conv
@@ -279,7 +312,7 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
     m_in0 / m_in1: optional active-row counts of the two sources (ints or 1-element device tensors), used only
     by the profiler's algorithmic-byte accounting.
 
-    x0: rows (R0, ld0); x1: optional dense rows (N*H*W, ld1); wpacked from pack_weight (taps*(c0+c1), ldw).
+    x0: rows (R0, ld0); x1: optional dense rows (N*H*W, ld1); wpacked: PackedW from pack_weight(weight, c1).
     Returns y rows (max_rows, pad4(cout)).
     """
     lib = _lib.load()
@@ -289,21 +322,23 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
     ldy = pad4(cout)
     if out is None:
         out = torch.empty((max(max_rows, 1), ldy), dtype=_f32, device=dev)
-    assert wpacked.shape[0] == taps * (c0 + c1), (wpacked.shape, taps, c0, c1)
+    assert isinstance(wpacked, PackedW) and (wpacked.taps, wpacked.c0, wpacked.c1, wpacked.cout) == (taps, c0, c1, cout), \
+        ((wpacked.taps, wpacked.c0, wpacked.c1, wpacked.cout), (taps, c0, c1, cout))
     d = _lib.ConvDesc()
     d.N, d.H, d.W = n, h, w
     d.x0, d.c0, d.ld0 = _lib.ptr(x0, _f32), c0, x0.shape[1]
     d.map0, d.shift0 = _lib.ptr(map0, _i32), shift0
     d.x1, d.c1, d.ld1 = (_lib.ptr(x1, _f32), c1, x1.shape[1]) if x1 is not None else (None, 0, 0)
     d.gate = _lib.ptr(gate, _u8)
-    d.w, d.bias = _lib.ptr(wpacked, _f32), _lib.ptr(bias, _f32)
-    d.cout, d.ldw, d.taps, d.pad_mode = cout, wpacked.shape[1], taps, pad
+    d.w, d.bias = _lib.ptr(wpacked.data, _f32), _lib.ptr(bias, _f32)
+    d.cout, d.ldw, d.taps, d.pad_mode = cout, (wpacked.data.shape[1] if wpacked.kind == "simt" else 0), taps, pad
     d.pixels, d.count, d.max_rows = _lib.ptr(pixels, _i32), _lib.ptr(count, _i32), max_rows
     d.y, d.ldy = _lib.ptr(out, _f32), out.shape[1]
     d.act, d.act_param = act, float(act_param)
-    with _prof('conv_rows', lambda: dict(n=n, h=h, w=w, taps=taps, c0=c0, c1=c1, cout=cout, shift0=shift0, count=count, max_rows=max_rows, m_in0=m_in0, m_in1=m_in1)):
-        rc = lib.wmd_conv_rows_f32(ctypes.byref(d), _lib.stream_ptr())
-    _lib.check(rc, "wmd_conv_rows_f32")
+    fn = lib.wmd_conv_rows_tc_f32 if wpacked.kind == "tc" else lib.wmd_conv_rows_f32
+    with _prof('conv_rows', lambda: dict(n=n, h=h, w=w, taps=taps, c0=c0, c1=c1, cout=cout, shift0=shift0, count=count, max_rows=max_rows, m_in0=m_in0, m_in1=m_in1, kind=wpacked.kind)):
+        rc = fn(ctypes.byref(d), _lib.stream_ptr())
+    _lib.check(rc, "wmd_conv_rows_%sf32" % ("tc_" if wpacked.kind == "tc" else ""))
     return out
 
 
