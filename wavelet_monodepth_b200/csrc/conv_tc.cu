@@ -1,22 +1,30 @@
 // K5-TC: the gather-GEMM convolution on 5th-gen tensor cores (tcgen05 + TMEM), fp32-faithful via 3xTF32.
 //
 // Same contract as conv_rows_kernel (conv.cu), different engine.  One CTA per SM owns a 256 x 128 output tile
-// (two UMMA M=128 halves sharing one B tile) and walks K = taps x (c0 + c1) in 32-channel chunks:
-//   * A (implicit im2col: 256 gathered rows x 32 channels) is fetched with 16-byte zero-filling cp.async straight
-//     into 128B-swizzled K-major shared-memory tiles - the layout a TMA tile load would have produced, which TMA
-//     cannot do here because the rows come from an index-map gather.  The 128-byte line of each row piece is
-//     prefetched into L2 several chunks ahead (prefetch.global.L2), so the cp.async itself is an L2 hit;
-//   * B (weights) is pre-split and pre-swizzled by wmd_pack_conv_weight_tc_f32 into one [hi | lo] image per
-//     (n-tile, chunk): a single 32 KB cp.async.bulk by one thread, completing on an mbarrier (async proxy);
-//   * each of the 16 warps' threads then splits exactly the 16-byte A pieces it copied (visible to it after
-//     cp.async.wait_group) into tf32 "hi" (in place) and "lo": x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi);
-//   * one elected thread issues per chunk 2 halves x 4 k-steps x 3 tcgen05.mma.kind::tf32 (lo*hi + hi*lo + hi*hi)
-//     into fp32 accumulators in TMEM and commits to an mbarrier that frees the stage (2-stage ring);
-//   * the tensor core's fp32 accumulation rounds toward zero, a bias that grows linearly with K (measured
-//     ~6.5e-9 * K relative).  So accumulation runs in EPOCHS of kFlushChunks chunks that alternate between two
-//     TMEM column sets; a finished epoch is drained (tcgen05.ld) into per-thread fp32 registers with ordinary
-//     round-to-nearest adds while the next epoch's MMAs run.  Each thread ends up owning one output row x 64
-//     channels: bias + activation + one contiguous 256-byte row store.
+// (two UMMA M=128 halves sharing one B tile) and walks K = taps x (c0 + c1) in 32-channel chunks.
+// Warp-specialised, mbarrier-pipelined (no CTA-wide barrier inside the K loop):
+//
+//   producers (warps 0-11)
+//     * gather A (implicit im2col: 256 rows x 32 channels) with 16-byte zero-filling cp.async into a raw fp32,
+//       128B-swizzled shared tile (lanes = adjacent pieces of a row: 4 lines per warp request; rows come from an
+//       index-map gather, which a TMA tile load cannot express), L2-prefetched a few chunks ahead;
+//     * then each thread owns (row, 8 channels) slots: reads them back (the swizzle makes this transposed read
+//       conflict-free), splits x = hi + lo (hi = x with the 13 low mantissa bits cleared, lo = x - hi: exact) and
+//       writes hi / lo into TENSOR MEMORY with tcgen05.st - the MMAs take A from TMEM (".ts" form), because an
+//       SS-mode M=128 x N=128 MMA would need the full 128 B/clk of shared-memory bandwidth three times per k-step;
+//   issuers (lane 0 of warps 12-15, one k-step each)
+//     * a single thread can only issue one tcgen05.mma per ~200 clk (measured, scripts/bench_cu/mma_rate.cu) while
+//       a 128x128x8 tf32 MMA occupies the tensor pipe for 64: four issuers keep it fed (83 % of peak in isolation);
+//     * per chunk each issues 2 halves x 3 terms (lo*hi + hi*lo + hi*hi) and commits to the mbarriers that recycle
+//       the TMEM A stage / shared B stage; B (weights) is pre-split, pre-swizzled by wmd_pack_conv_weight_tc_f32
+//       into one [hi | lo] image per (n-tile, chunk): a single 32 KB cp.async.bulk into a 4-deep ring;
+//   all 16 warps
+//     * the tensor core's fp32 accumulation rounds toward zero, a bias that grows linearly with K (measured
+//       ~6.5e-9 * K relative).  So accumulation runs in EPOCHS of kFlushChunks chunks: a finished epoch is drained
+//       (tcgen05.ld) into per-thread fp32 registers with round-to-nearest adds and the TMEM accumulators are
+//       re-zeroed.  Each thread ends up owning one output row x 64 channels: bias + activation + one 256-byte store.
+// TMEM map (512 columns): [0,256) accumulators (half h at h*128), [256,512) A operand: stage s, half h at
+// 256 + s*128 + h*64, hi in the first 32 columns, lo in the next 32.
 #include "common.cuh"
 
 namespace wmd {
@@ -24,27 +32,43 @@ namespace wmd {
 constexpr int TC_BM = 256;                      // rows per CTA tile = 2 UMMA halves of 128
 constexpr int TC_BN = 128;
 constexpr int TC_BK = 32;                       // floats per chunk = one 128-byte swizzle-atom row
-constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 512;                 // 16 warps: all gather/split; warp w drains TMEM lane quarter w&3
-constexpr int TC_A_HALF = 128 * TC_BK * 4;      // 16 KB: one M=128 half of A (hi or lo)
+constexpr int TC_THREADS = 512;                 // 16 warps: 12 producers + 4 issuers; all drain (lane quarter w&3, half (w>>2)&1, cols w>>3)
+constexpr int TC_PROD_WARPS = 12;
+constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
+#ifndef WMD_TC_ISSUERS
+#define WMD_TC_ISSUERS 2
+#endif
+constexpr int TC_ISSUERS = WMD_TC_ISSUERS;      // issuer i handles k-steps i, i+TC_ISSUERS, ... of every chunk
+constexpr int TC_A_STAGES = 2;                  // raw A tiles in shared memory (and split A stages in TMEM)
+constexpr int TC_B_STAGES = 4;                  // [Bhi | Blo] images in shared memory
+constexpr int TC_A_TILE = TC_BM * TC_BK * 4;    // 32 KB raw fp32
 constexpr int TC_B_TILE = TC_BN * TC_BK * 4;    // 16 KB (hi or lo)
-constexpr int TC_STAGE = 4 * TC_A_HALF + 2 * TC_B_TILE;            // [A0hi A1hi A0lo A1lo Bhi Blo] = 96 KB
 constexpr int TC_TABLES = 2 * 9 * TC_BM * 4;
-constexpr size_t TC_SMEM = static_cast<size_t>(TC_STAGES) * TC_STAGE + TC_TABLES + 1024;
-constexpr int TC_TMEM_COLS = 512;               // 2 epoch sets x 2 halves x 128 columns
+constexpr size_t TC_SMEM = static_cast<size_t>(TC_A_STAGES) * TC_A_TILE + static_cast<size_t>(TC_B_STAGES) * 2 * TC_B_TILE +
+                           TC_TABLES + 1024;
+constexpr int TC_TMEM_COLS = 512;
 constexpr int kFlushChunks = 32;                // epoch length: K = 1024 per TMEM accumulation run
 constexpr int kPrefetchAhead = 4;               // chunks of L2 prefetch distance
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;        // tap-table entry of an inactive / padded source
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
 }
+#ifdef WMD_TC_DEBUG
+__device__ unsigned int g_dbg[4];
+#define MBAR_FAIL(id) do { if (atomicCAS(&g_dbg[0], 0u, (id)) == 0u) { g_dbg[1] = blockIdx.x; g_dbg[2] = threadIdx.x; } return; } while (0)
+#define MBAR_SPINS (1u << 21)
+#else
+#define MBAR_FAIL(id) __trap()
+#define MBAR_SPINS (1u << 28)
+#endif
 // bounded spin: a protocol bug traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t id = 0) {
   uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+  for (uint32_t spin = 0; spin < MBAR_SPINS; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -54,8 +78,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (done) return;
   }
-  __trap();
+  MBAR_FAIL(id);
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void producer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(TC_PROD_THREADS) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -73,12 +101,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+// D[tmem] (+)= A[tmem] * B[smem]^T : A is 128 lanes x 8 tf32 columns in tensor memory, B a K-major smem tile
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -91,16 +120,19 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
-// in place: *ph <- hi, *pl <- lo
-__device__ __forceinline__ void split_piece(float4* ph, float4* pl) {
-  const float4 v = *ph;
-  float4 h, l;
-  h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
-  h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
-  h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
-  h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
-  *ph = h;
-  *pl = l;
+// this thread's TMEM lane (warp quarter base + lane), 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr),
+      "r"(z)
+      : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -127,23 +159,27 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_conv_desc d, const float* __restrict__ wtc) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) uint64_t bar_mma[TC_STAGES];     // stage consumed by the tensor pipe
-  __shared__ __align__(8) uint64_t bar_b[TC_STAGES];       // weight image of the stage has landed (bulk copy)
-  __shared__ __align__(8) uint64_t bar_epoch[2];           // accumulation epoch complete (per TMEM set)
+  __shared__ __align__(8) uint64_t bar_asplit[2];          // split A of the TMEM stage is stored (12 producer warps)
+  __shared__ __align__(8) uint64_t bar_mma[2];             // chunk's MMAs done (4 issuers): TMEM A stage + B stage reusable
+  __shared__ __align__(8) uint64_t bar_b[TC_B_STAGES];     // weight image of the stage has landed (bulk copy)
+  __shared__ __align__(8) uint64_t bar_epoch;              // accumulation epoch complete (4 issuers)
   __shared__ uint32_t tmem_base_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_producer = warp < TC_PROD_WARPS;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint32_t* tab0 = reinterpret_cast<uint32_t*>(base + TC_STAGES * TC_STAGE);   // 16-byte-unit offsets into x0
-  uint32_t* tab1 = tab0 + 9 * TC_BM;                                            // ... into x1
+  unsigned char* sA_base = base;
+  unsigned char* sB_base = base + TC_A_STAGES * TC_A_TILE;
+  uint32_t* tab0 = reinterpret_cast<uint32_t*>(sB_base + TC_B_STAGES * 2 * TC_B_TILE);   // 16-byte-unit offsets into x0
+  uint32_t* tab1 = tab0 + 9 * TC_BM;                                                      // ... into x1
 
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_mma[s]), 1);
-      mbar_init(smem_u32(&bar_b[s]), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_asplit[s]), TC_PROD_WARPS);
+      mbar_init(smem_u32(&bar_mma[s]), TC_ISSUERS);
     }
-    mbar_init(smem_u32(&bar_epoch[0]), 1);
-    mbar_init(smem_u32(&bar_epoch[1]), 1);
+    for (int s = 0; s < TC_B_STAGES; ++s) mbar_init(smem_u32(&bar_b[s]), 1);
+    mbar_init(smem_u32(&bar_epoch), TC_ISSUERS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -173,26 +209,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(TC_BN >> 3) << 17) |
                               (static_cast<uint32_t>(128 >> 4) << 24);
 
-  // UMMA descriptors are loop invariant up to a +2 (32 bytes >> 4) per k-step in the start-address field: build
-  // them once so the single issuing thread spends ~3 instructions per tcgen05.mma instead of ~30
-  uint64_t dsc[TC_STAGES][6];   // [A0hi A1hi A0lo A1lo Bhi Blo]
-#pragma unroll
-  for (int s = 0; s < TC_STAGES; ++s) {
-    const uint32_t sA = smem_u32(base + s * TC_STAGE);
-    dsc[s][0] = umma_desc_sw128(sA);
-    dsc[s][1] = umma_desc_sw128(sA + TC_A_HALF);
-    dsc[s][2] = umma_desc_sw128(sA + 2 * TC_A_HALF);
-    dsc[s][3] = umma_desc_sw128(sA + 3 * TC_A_HALF);
-    dsc[s][4] = umma_desc_sw128(sA + 4 * TC_A_HALF);
-    dsc[s][5] = umma_desc_sw128(sA + 4 * TC_A_HALF + TC_B_TILE);
-  }
-
-  // producer mapping: thread -> 16-byte piece a_j of rows a_r0 + 64*i (i < 4); row r lives in half r>>7
-  const int a_j = tid & 7, a_r0 = tid >> 3;
-  uint32_t use0 = 0, use1 = 0;                 // MMA commits issued so far per stage (phase tracking)
-  uint32_t ep_use0 = 0, ep_use1 = 0;           // epoch commits per TMEM set
-  // accumulator ownership: TMEM lane quarter, M half, 64-column half
+  // drain / store ownership (all 16 warps): TMEM lane quarter, M half, 64-column half
   const int my_q = warp & 3, my_half = (warp >> 2) & 1, my_ch = warp >> 3;
+  const int my_row = my_half * 128 + my_q * 32 + lane;          // row within the CTA tile
+  const uint32_t lane_field = static_cast<uint32_t>(my_q * 32) << 16;
+  const uint32_t my_acc_addr = tmem_acc + lane_field + static_cast<uint32_t>(my_half * 128 + my_ch * 64);
+  uint32_t mma_rounds = 0;                                       // chunks issued so far by this CTA (all tiles)
+  uint32_t epochs = 0;                                           // epoch commits so far
+
+  // accumulators start (and are left by every drain) at zero: every MMA accumulates
+  tmem_zero32(my_acc_addr);
+  tmem_zero32(my_acc_addr + 32u);
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int m0 = static_cast<int>(tile / n_tiles) * TC_BM;
@@ -235,140 +266,201 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
 
     const unsigned char* wtile = reinterpret_cast<const unsigned char*>(wtc) +
                                  static_cast<long long>(nt) * nchunks * (2 * TC_B_TILE);
-
-    // decode chunk c -> gather source (as float4 pointer), channels left, offset table
-    auto chunk_src = [&](int c, const float4*& xq, int& cleft) -> const uint32_t* {
-      const int tap = c / per_tap;
-      const int rr = c - tap * per_tap;
-      const bool src1 = rr >= nch0;
-      const int ci0 = (src1 ? rr - nch0 : rr) * TC_BK;
-      cleft = (src1 ? d.c1 : d.c0) - ci0;                                   // channels available from ci0 on
-      xq = reinterpret_cast<const float4*>(src1 ? d.x1 : d.x0) + (ci0 >> 2);
-      return (src1 ? tab1 : tab0) + tap * TC_BM;
-    };
-
-    auto prefetch_chunk = [&](int c) {
-      if (a_j != 0) return;                      // one 128-byte line per row
-      const float4* xq; int cleft;
-      const uint32_t* tab = chunk_src(c, xq, cleft);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t off = tab[a_r0 + 64 * i];
-        if (off != kNoRow) prefetch_l2(xq + off);
-      }
-    };
-
-    auto load_chunk = [&](int c, int stage) {
-      const float4* xq; int cleft;
-      const uint32_t* tab = chunk_src(c, xq, cleft);
-      unsigned char* sA = base + stage * TC_STAGE;
-      const int a_bytes = max(0, min(16, (cleft - a_j * 4) * 4));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = a_r0 + 64 * i;             // 0..255; half = r >> 7
-        const uint32_t off = tab[r];
-        const bool live = off != kNoRow && a_bytes > 0;
-        const float4* src = live ? xq + off + a_j : xq;
-        cp_async16(sA + (r >> 7) * TC_A_HALF + (r & 127) * 128 + ((a_j ^ (r & 7)) << 4), src, live ? a_bytes : 0);
-      }
-      // weights: pre-split, pre-swizzled [Bhi | Blo] image of (n-tile, chunk): one 32 KB bulk copy
-      if (tid == 0)
-        bulk_g2s(smem_u32(sA + 4 * TC_A_HALF), wtile + static_cast<long long>(c) * (2 * TC_B_TILE), 2 * TC_B_TILE,
-                 smem_u32(&bar_b[stage]));
-    };
-
-    auto split_chunk = [&](int stage) {
-      unsigned char* sA = base + stage * TC_STAGE;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = a_r0 + 64 * i;
-        unsigned char* p = sA + (r >> 7) * TC_A_HALF + (r & 127) * 128 + ((a_j ^ (r & 7)) << 4);
-        split_piece(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(p + 2 * TC_A_HALF));
-      }
-    };
+    const uint32_t round0 = mma_rounds;
 
     float acc[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) acc[j] = 0.f;
 
-    // drains this thread's slice (its row, 64 columns) of TMEM set `set` into acc with round-to-nearest adds
-    auto drain = [&](int set) {
-      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(my_q * 32) << 16) +
-                             static_cast<uint32_t>(set * 256 + my_half * 128 + my_ch * 64);
+    // drains this thread's slice (its row, 64 columns) with round-to-nearest adds and re-zeroes it
+    auto drain = [&]() {
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 32) {
         uint32_t v[32];
-        tmem_ld32(taddr + cc, v);
+        tmem_ld32(my_acc_addr + cc, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[cc + j] += __uint_as_float(v[j]);
+        tmem_zero32(my_acc_addr + cc);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
     };
 
-    // ---- prologue: first chunk in flight, first prefetches
-    for (int c = 1; c <= kPrefetchAhead && c < nchunks; ++c) prefetch_chunk(c);
-    if (use0 > 0) mbar_wait(smem_u32(&bar_mma[0]), (use0 - 1) & 1);     // previous tile's MMAs left stage 0
-    load_chunk(0, 0);
-    cp_async_commit();
-
-    for (int c = 0; c < nchunks; ++c) {
-      const int stage = c & 1;
-      const int epoch = c / kFlushChunks, set = epoch & 1;
-      const uint32_t fills = (stage == 0) ? use0 : use1;     // loads into this stage before this one == MMA rounds so far
-      cp_async_wait<0>();
-      split_chunk(stage);
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(smem_u32(&bar_b[stage]), fills & 1);        // this stage's weight image has landed
-        tc_fence_after();
-        const bool first = (c % kFlushChunks) == 0;
-        const uint64_t* ds = stage == 0 ? dsc[0] : dsc[1];
+    if (is_producer) {
+      // =================================================================================== producers
+      // decode chunk c -> gather source (as float4 pointer), channels left, offset table
+      auto chunk_src = [&](int c, const float4*& xq, int& cleft) -> const uint32_t* {
+        const int tap = c / per_tap;
+        const int rr = c - tap * per_tap;
+        const bool src1 = rr >= nch0;
+        const int ci0 = (src1 ? rr - nch0 : rr) * TC_BK;
+        cleft = (src1 ? d.c1 : d.c0) - ci0;
+        xq = reinterpret_cast<const float4*>(src1 ? d.x1 : d.x0) + (ci0 >> 2);
+        return (src1 ? tab1 : tab0) + tap * TC_BM;
+      };
+      auto prefetch_chunk = [&](int c) {
+        const float4* xq; int cleft;
+        const uint32_t* tab = chunk_src(c, xq, cleft);
+        if (tid < TC_BM) {                          // one 128-byte line per row
+          const uint32_t off = tab[tid];
+          if (off != kNoRow) prefetch_l2(xq + off);
+        }
+      };
+      // raw fp32 A tile of chunk c -> shared A stage c&1 (128B-swizzled rows); 2048 pieces over 384 threads
+      auto load_a = [&](int c) {
+        const float4* xq; int cleft;
+        const uint32_t* tab = chunk_src(c, xq, cleft);
+        unsigned char* sA = sA_base + (c & 1) * TC_A_TILE;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t dcol = tmem_acc + static_cast<uint32_t>(set * 256 + half * 128);
-#pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t ko = static_cast<uint64_t>(2 * k);   // 8 tf32 = 32 bytes along K inside the swizzle atom
-            umma_tf32(dcol, ds[2 + half] + ko, ds[4] + ko, kIdesc, (first && k == 0) ? 0u : 1u);   // lo*hi first
-            umma_tf32(dcol, ds[half] + ko, ds[5] + ko, kIdesc, 1u);                                   // hi*lo
-            umma_tf32(dcol, ds[half] + ko, ds[4] + ko, kIdesc, 1u);                                   // hi*hi
+        for (int i = 0; i < 6; ++i) {
+          const int p = tid + i * TC_PROD_THREADS;
+          if (p < TC_BM * 8) {
+            const int r = p >> 3, j = p & 7;
+            const int a_bytes = max(0, min(16, (cleft - j * 4) * 4));
+            const uint32_t off = tab[r];
+            const bool live = off != kNoRow && a_bytes > 0;
+            const float4* src = live ? xq + off + j : xq;
+            cp_async16(sA + r * 128 + ((j ^ (r & 7)) << 4), src, live ? a_bytes : 0);
           }
         }
-        umma_commit(smem_u32(&bar_mma[stage]));
-        if ((c + 1) % kFlushChunks == 0 || c == nchunks - 1) umma_commit(smem_u32(&bar_epoch[set]));
-      }
-      if (stage == 0) use0 += 1; else use1 += 1;
-      const bool epoch_end = ((c + 1) % kFlushChunks == 0) || (c == nchunks - 1);
-      if (epoch_end) { if (set == 0) ep_use0 += 1; else ep_use1 += 1; }
+      };
 
-      // refill the other stage (chunk c+1) once chunk c-1's MMAs have drained it; keep L2 warm further ahead
-      if (c + 1 < nchunks) {
-        const uint32_t u = (stage == 0) ? use1 : use0;
-        if (u > 0) mbar_wait(smem_u32(&bar_mma[stage ^ 1]), (u - 1) & 1);
-        load_chunk(c + 1, stage ^ 1);
-        if (c + 1 + kPrefetchAhead < nchunks) prefetch_chunk(c + 1 + kPrefetchAhead);
-      }
+      for (int c = 1; c <= kPrefetchAhead && c < nchunks; ++c) prefetch_chunk(c);
+      load_a(0);
       cp_async_commit();
 
-      // a finished epoch (other than the last, handled below) is drained while the next epoch's MMAs run
-      if (epoch_end && c != nchunks - 1) {
-        const uint32_t eu = (set == 0) ? ep_use0 : ep_use1;
-        mbar_wait(smem_u32(&bar_epoch[set]), (eu - 1) & 1);
+      const int wt = warp >> 2;                      // 0..2: which of the quarter's three producer warps
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t round = round0 + c;
+        const uint32_t tstage = round & 1;
+        cp_async_wait<0>();
+        producer_barrier();                          // raw A tile of chunk c complete; split reads of chunk c-1 done
+        if (c + 1 < nchunks) {
+          load_a(c + 1);
+          if (c + 1 + kPrefetchAhead < nchunks) prefetch_chunk(c + 1 + kPrefetchAhead);
+        }
+        cp_async_commit();
+        if ((c % kFlushChunks) == 0 && c > 0) {      // epoch boundary: everybody drains before the next epoch starts
+          mbar_wait(smem_u32(&bar_epoch), (epochs - 1) & 1, 0x10000u + round);
+          tc_fence_after();
+          drain();
+          tc_fence_before();
+          __syncthreads();
+          tc_fence_after();
+        }
+        // TMEM A stage free?  It was read by the MMAs of round-2.
+        if (round >= 2) mbar_wait(smem_u32(&bar_mma[tstage]), ((round - 2) >> 1) & 1, 0x20000u + round);
         tc_fence_after();
-        drain(set);
+        // split my (row, 8 channels) slots: u = half*4 + channel-quarter, u = wt, wt+3, wt+6
+        {
+          const unsigned char* tile_a = sA_base + (c & 1) * TC_A_TILE;
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const int slot = wt + 3 * u;
+            if (slot < 8) {
+              const int h = slot >> 2, kq = slot & 3;
+              const int r = h * 128 + my_q * 32 + lane;
+              const unsigned char* rowp = tile_a + r * 128;
+              const uint4 v0 = *reinterpret_cast<const uint4*>(rowp + (((2 * kq) ^ (r & 7)) << 4));
+              const uint4 v1 = *reinterpret_cast<const uint4*>(rowp + (((2 * kq + 1) ^ (r & 7)) << 4));
+              const uint32_t raw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                hi[e] = raw[e] & 0xFFFFE000u;                                       // tf32 by truncation
+                lo[e] = __float_as_uint(__uint_as_float(raw[e]) - __uint_as_float(hi[e]));   // exact remainder
+              }
+              const uint32_t ta = tmem_acc + lane_field + 256u + tstage * 128u + static_cast<uint32_t>(h * 64 + kq * 8);
+              tmem_st8(ta, hi);
+              tmem_st8(ta + 32u, lo);
+            }
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        }
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_asplit[tstage]));
+        if (((c + 1) % kFlushChunks == 0) || (c == nchunks - 1)) epochs += 1;
+      }
+    } else {
+      // =================================================================================== issuers
+      const int kstep = warp - TC_PROD_WARPS;        // this issuer's k-step inside every chunk
+      if (kstep == 0 && lane == 0) {
+        bulk_g2s(smem_u32(sB_base + (round0 % TC_B_STAGES) * 2 * TC_B_TILE), wtile, 2 * TC_B_TILE,
+                 smem_u32(&bar_b[round0 % TC_B_STAGES]));
+        if (nchunks > 1)
+          bulk_g2s(smem_u32(sB_base + ((round0 + 1) % TC_B_STAGES) * 2 * TC_B_TILE), wtile + 2 * TC_B_TILE, 2 * TC_B_TILE,
+                   smem_u32(&bar_b[(round0 + 1) % TC_B_STAGES]));
+      }
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t round = round0 + c;
+        const uint32_t tstage = round & 1;
+        const uint32_t bs = round % TC_B_STAGES;
+        if ((c % kFlushChunks) == 0 && c > 0) {      // epoch boundary (all lanes: drain is warp-collective)
+          mbar_wait(smem_u32(&bar_epoch), (epochs - 1) & 1);
+          tc_fence_after();
+          drain();
+          tc_fence_before();
+          __syncthreads();
+          tc_fence_after();
+        }
+        if (lane == 0 && kstep < TC_ISSUERS) {
+          mbar_wait(smem_u32(&bar_asplit[tstage]), (round >> 1) & 1, 0x30000u + round);           // split A of this chunk is in TMEM
+          mbar_wait(smem_u32(&bar_b[bs]), (round / TC_B_STAGES) & 1, 0x40000u + round);           // weight image has landed
+          tc_fence_after();
+          const uint64_t b0 = umma_desc_sw128(smem_u32(sB_base + bs * 2 * TC_B_TILE));
+#if WMD_TC_ISSUERS == 2
+          // deterministic partition: issuer h owns the accumulator of M-half h (one writer per accumulator, so the
+          // order of the round-toward-zero accumulations - and therefore every output bit - is fixed)
+          {
+            const uint32_t dh = tmem_acc + static_cast<uint32_t>(kstep * 128);
+            const uint32_t ah = tmem_acc + 256u + tstage * 128u + static_cast<uint32_t>(kstep * 64);
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+              const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
+              const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
+              const uint32_t a = ah + static_cast<uint32_t>(8 * ks);
+              umma_tf32_ts(dh, a + 32u, bh, kIdesc, 1u);     // lo*hi
+              umma_tf32_ts(dh, a, bl, kIdesc, 1u);           // hi*lo
+              umma_tf32_ts(dh, a, bh, kIdesc, 1u);           // hi*hi
+            }
+          }
+#else
+          for (int ks = kstep; ks < TC_BK / 8; ks += TC_ISSUERS) {
+            const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
+            const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
+            const uint32_t a0 = tmem_acc + 256u + tstage * 128u + static_cast<uint32_t>(8 * ks), a1 = a0 + 64u;
+            const uint32_t d0 = tmem_acc, d1 = tmem_acc + 128u;
+            umma_tf32_ts(d0, a0 + 32u, bh, kIdesc, 1u);     // lo*hi
+            umma_tf32_ts(d1, a1 + 32u, bh, kIdesc, 1u);
+            umma_tf32_ts(d0, a0, bl, kIdesc, 1u);           // hi*lo
+            umma_tf32_ts(d1, a1, bl, kIdesc, 1u);
+            umma_tf32_ts(d0, a0, bh, kIdesc, 1u);           // hi*hi
+            umma_tf32_ts(d1, a1, bh, kIdesc, 1u);
+          }
+#endif
+          umma_commit(smem_u32(&bar_mma[tstage]));
+          if (((c + 1) % kFlushChunks == 0) || (c == nchunks - 1)) umma_commit(smem_u32(&bar_epoch));
+          // weights two chunks ahead: that B stage was last read by round-2, and all of round-2's MMAs are known to
+          // be complete - the producers only stored this chunk's A (bar_asplit, awaited above) after bar_mma(round-2).
+          // (Waiting on bar_mma here would alias: this round's own commits may already have flipped its phase.)
+          if (kstep == 0 && c + 2 < nchunks) {
+            const uint32_t ns = (round + 2) % TC_B_STAGES;
+            bulk_g2s(smem_u32(sB_base + ns * 2 * TC_B_TILE), wtile + static_cast<long long>(c + 2) * (2 * TC_B_TILE),
+                     2 * TC_B_TILE, smem_u32(&bar_b[ns]));
+          }
+        }
+        __syncwarp();
+        if (((c + 1) % kFlushChunks == 0) || (c == nchunks - 1)) epochs += 1;
       }
     }
-    cp_async_wait<0>();
+    mma_rounds = round0 + static_cast<uint32_t>(nchunks);
 
-    // ---- last epoch + epilogue: bias, activation, one contiguous 256-byte store per thread
+    // ---- last epoch + epilogue (all 16 warps): bias, activation, one contiguous 256-byte store per thread
     {
-      const int set = ((nchunks - 1) / kFlushChunks) & 1;
-      const uint32_t eu = (set == 0) ? ep_use0 : ep_use1;
-      mbar_wait(smem_u32(&bar_epoch[set]), (eu - 1) & 1);
+      mbar_wait(smem_u32(&bar_epoch), (epochs - 1) & 1, 0x60000u + mma_rounds);
       tc_fence_after();
-      drain(set);
-      const int m = m0 + my_half * 128 + my_q * 32 + lane;
+      drain();
+      const int m = m0 + my_row;
       if (m < rows) {
         float* yr = d.y + static_cast<long long>(m) * d.ldy;
         const bool vec_ok = (d.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0);
@@ -394,7 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       }
     }
     tc_fence_before();
-    __syncthreads();   // accumulators drained by every warp, tap tables free
+    __syncthreads();   // accumulators drained + re-zeroed by every warp, tap tables free
     tc_fence_after();
   }
 
@@ -444,6 +536,13 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
 }
 
 }  // namespace wmd
+
+
+#ifdef WMD_TC_DEBUG
+extern "C" int wmd_debug_read(unsigned int* host) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host, wmd::g_dbg, sizeof(unsigned int) * 4));
+}
+#endif
 
 extern "C" int wmd_conv_tc_tile_n(int cout) { (void)cout; return wmd::TC_BN; }
 
