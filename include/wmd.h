@@ -160,10 +160,10 @@ int wmd_conv_rows_f32(const wmd_conv_desc* d, wmd_stream_t stream);
 /* Tensor-core engine for the same contract: tcgen05.mma.kind::tf32 with a 3xTF32 split (hi*hi + lo*hi + hi*lo,
  * fp32 accumulation in TMEM), so results stay fp32-faithful (<= ~1e-6 relative vs the SIMT kernel).  d->w must
  * point to weights packed by wmd_pack_conv_weight_tc_f32 for the same (cout, c0, c1, taps); d->ldw is ignored.
- *   wmd_conv_tc_tile_n(cout)                 N-tile of the kernel (128; the CTA tile is 256 rows x 128 channels)
+ *   wmd_conv_tc_tile_n(cout)                 N-tile of the kernel for this cout (128 / 64 / 32; the CTA tile is 256 rows x N)
  *   wmd_conv_tc_weight_floats(...)           size of the packed weight buffer, in floats
  *   wmd_pack_conv_weight_tc_f32(w, packed..) (Cout, c0+c1, kh, kw) -> per (n-tile, 32-channel chunk) fp32
- *                                            shared-memory images [128 x 32], K-major, 128-byte swizzled
+ *                                            shared-memory images [tf32 hi | tf32 lo] of N x 32, K-major, 128-byte swizzled
  * Accumulation runs in epochs of K = 1024 inside TMEM and is drained into fp32 registers with round-to-nearest
  * adds, because the tensor core's own fp32 accumulation rounds toward zero (bias ~6.5e-9 * K relative). */
 int wmd_conv_tc_tile_n(int cout);

@@ -15,7 +15,7 @@ REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libwmd.so")
 
-NVCC_FLAGS = (["-DWMD_TC_DEBUG"] if os.environ.get("WMD_TC_DEBUG") else []) + (["-DWMD_TC_ISSUERS=" + os.environ["WMD_TC_ISSUERS"]] if os.environ.get("WMD_TC_ISSUERS") else []) + [
+NVCC_FLAGS = (["-DWMD_TC_DEBUG"] if os.environ.get("WMD_TC_DEBUG") else []) + [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
 ]

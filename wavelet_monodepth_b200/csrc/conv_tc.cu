@@ -30,23 +30,30 @@
 namespace wmd {
 
 constexpr int TC_BM = 256;                      // rows per CTA tile = 2 UMMA halves of 128
-constexpr int TC_BN = 128;
 constexpr int TC_BK = 32;                       // floats per chunk = one 128-byte swizzle-atom row
 constexpr int TC_THREADS = 512;                 // 16 warps: 12 producers + 4 issuers; all drain (lane quarter w&3, half (w>>2)&1, cols w>>3)
 constexpr int TC_PROD_WARPS = 12;
 constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
-#ifndef WMD_TC_ISSUERS
-#define WMD_TC_ISSUERS 2
-#endif
-constexpr int TC_ISSUERS = WMD_TC_ISSUERS;      // issuer i handles k-steps i, i+TC_ISSUERS, ... of every chunk
 constexpr int TC_A_STAGES = 2;                  // raw A tiles in shared memory (and split A stages in TMEM)
 constexpr int TC_B_STAGES = 4;                  // [Bhi | Blo] images in shared memory
 constexpr int TC_A_TILE = TC_BM * TC_BK * 4;    // 32 KB raw fp32
-constexpr int TC_B_TILE = TC_BN * TC_BK * 4;    // 16 KB (hi or lo)
 constexpr int TC_TABLES = 2 * 9 * TC_BM * 4;
-constexpr size_t TC_SMEM = static_cast<size_t>(TC_A_STAGES) * TC_A_TILE + static_cast<size_t>(TC_B_STAGES) * 2 * TC_B_TILE +
-                           TC_TABLES + 1024;
 constexpr int TC_TMEM_COLS = 512;
+
+// Per N-tile configuration.  A single thread issues one tcgen05.mma per ~200 clk whatever its size, so narrow
+// tiles need more issuers to keep the tensor pipe fed; every issuer gets a PRIVATE accumulator copy (one writer per
+// accumulator => the order of the round-toward-zero accumulations, and with it every output bit, is fixed) and the
+// copies are summed in registers at drain time.  Accumulators: (half h, copy j) at column (h*COPIES + j)*BN <= 256.
+template <int BN>
+struct TcCfg {
+  static constexpr int COPIES = BN >= 128 ? 1 : 2;
+  static constexpr int ISSUERS = 2 * COPIES;               // issuer i: half i / COPIES, k-steps (i % COPIES) + n*COPIES
+  static constexpr int B_TILE = BN * TC_BK * 4;            // bytes of one of hi / lo
+  static constexpr int ACC = BN / 2;                       // accumulator registers per thread: its row x BN/2 columns
+  static constexpr size_t SMEM = static_cast<size_t>(TC_A_STAGES) * TC_A_TILE +
+                                 static_cast<size_t>(TC_B_STAGES) * 2 * B_TILE + TC_TABLES + 1024;
+  static_assert(2 * COPIES * BN <= 256, "accumulators must leave 256 TMEM columns for the A operand");
+};
 constexpr int kFlushChunks = 32;                // epoch length: K = 1024 per TMEM accumulation run
 constexpr int kPrefetchAhead = 4;               // chunks of L2 prefetch distance
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;        // tap-table entry of an inactive / padded source
@@ -126,24 +133,19 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
   const uint32_t z = 0u;
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr),
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr),
       "r"(z)
       : "memory");
 }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
@@ -157,7 +159,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       : "memory");
 }
 
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_conv_desc d, const float* __restrict__ wtc) {
+  using Cfg = TcCfg<BN>;
+  constexpr int TC_B_TILE = Cfg::B_TILE;
+  constexpr int TC_ISSUERS = Cfg::ISSUERS;
+  constexpr int COPIES = Cfg::COPIES;
+  constexpr int ACC = Cfg::ACC;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t bar_asplit[2];          // split A of the TMEM stage is stored (12 producer warps)
   __shared__ __align__(8) uint64_t bar_mma[2];             // chunk's MMAs done (4 issuers): TMEM A stage + B stage reusable
@@ -200,26 +208,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   const int nch0 = (d.c0 + TC_BK - 1) / TC_BK, nch1 = (d.c1 + TC_BK - 1) / TC_BK;
   const int per_tap = nch0 + nch1;
   const int nchunks = d.taps * per_tap;
-  const int n_tiles = (d.cout + TC_BN - 1) / TC_BN;
+  const int n_tiles = (d.cout + BN - 1) / BN;
   const long long tiles = static_cast<long long>((rows + TC_BM - 1) / TC_BM) * n_tiles;
   const int Hs = d.H >> d.shift0, Ws = d.W >> d.shift0;
   const bool aligned_rows = (d.taps == 1 && d.map0 == nullptr);
   const uint32_t ld0q = static_cast<uint32_t>(d.ld0 >> 2), ld1q = static_cast<uint32_t>(d.ld1 >> 2);
-  // instruction descriptor: D=f32, A=B=tf32, both K-major, N = 128, M = 128
-  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(TC_BN >> 3) << 17) |
+  // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
+  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                               (static_cast<uint32_t>(128 >> 4) << 24);
 
-  // drain / store ownership (all 16 warps): TMEM lane quarter, M half, 64-column half
+  // drain / store ownership (all 16 warps): TMEM lane quarter, M half, column half (ACC = BN/2 columns of every copy)
   const int my_q = warp & 3, my_half = (warp >> 2) & 1, my_ch = warp >> 3;
   const int my_row = my_half * 128 + my_q * 32 + lane;          // row within the CTA tile
   const uint32_t lane_field = static_cast<uint32_t>(my_q * 32) << 16;
-  const uint32_t my_acc_addr = tmem_acc + lane_field + static_cast<uint32_t>(my_half * 128 + my_ch * 64);
+  const uint32_t my_acc_addr = tmem_acc + lane_field + static_cast<uint32_t>(my_half * COPIES * BN + my_ch * ACC);
   uint32_t mma_rounds = 0;                                       // chunks issued so far by this CTA (all tiles)
   uint32_t epochs = 0;                                           // epoch commits so far
 
   // accumulators start (and are left by every drain) at zero: every MMA accumulates
-  tmem_zero32(my_acc_addr);
-  tmem_zero32(my_acc_addr + 32u);
+#pragma unroll
+  for (int j = 0; j < COPIES; ++j)
+#pragma unroll
+    for (int cc = 0; cc < ACC; cc += 16) tmem_zero16(my_acc_addr + static_cast<uint32_t>(j * BN + cc));
   asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int m0 = static_cast<int>(tile / n_tiles) * TC_BM;
     const int nt = static_cast<int>(tile % n_tiles);
-    const int n0 = nt * TC_BN;
+    const int n0 = nt * BN;
 
     for (int e = tid; e < d.taps * TC_BM; e += TC_THREADS) {
       const int tap = e / TC_BM, r = e - tap * TC_BM;
@@ -268,19 +278,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
                                  static_cast<long long>(nt) * nchunks * (2 * TC_B_TILE);
     const uint32_t round0 = mma_rounds;
 
-    float acc[64];
+    float acc[ACC];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int j = 0; j < ACC; ++j) acc[j] = 0.f;
 
-    // drains this thread's slice (its row, 64 columns) with round-to-nearest adds and re-zeroes it
+    // drains this thread's slice (its row, ACC columns of every issuer's copy) with round-to-nearest adds, re-zeroes it
     auto drain = [&]() {
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        uint32_t v[32];
-        tmem_ld32(my_acc_addr + cc, v);
+      for (int cp = 0; cp < COPIES; ++cp) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[cc + j] += __uint_as_float(v[j]);
-        tmem_zero32(my_acc_addr + cc);
+        for (int cc = 0; cc < ACC; cc += 16) {
+          uint32_t v[16];
+          tmem_ld16(my_acc_addr + static_cast<uint32_t>(cp * BN + cc), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[cc + j] += __uint_as_float(v[j]);
+          tmem_zero16(my_acc_addr + static_cast<uint32_t>(cp * BN + cc));
+        }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
     };
@@ -408,14 +421,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           mbar_wait(smem_u32(&bar_b[bs]), (round / TC_B_STAGES) & 1, 0x40000u + round);           // weight image has landed
           tc_fence_after();
           const uint64_t b0 = umma_desc_sw128(smem_u32(sB_base + bs * 2 * TC_B_TILE));
-#if WMD_TC_ISSUERS == 2
-          // deterministic partition: issuer h owns the accumulator of M-half h (one writer per accumulator, so the
-          // order of the round-toward-zero accumulations - and therefore every output bit - is fixed)
-          {
-            const uint32_t dh = tmem_acc + static_cast<uint32_t>(kstep * 128);
-            const uint32_t ah = tmem_acc + 256u + tstage * 128u + static_cast<uint32_t>(kstep * 64);
+          // issuer -> (M half, accumulator copy); it alone writes that accumulator
+          const int ih = kstep / COPIES, icp = kstep % COPIES;
+          const uint32_t dh = tmem_acc + static_cast<uint32_t>((ih * COPIES + icp) * BN);
+          const uint32_t ah = tmem_acc + 256u + tstage * 128u + static_cast<uint32_t>(ih * 64);
 #pragma unroll
-            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            if ((ks % COPIES) == icp) {
               const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
               const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
               const uint32_t a = ah + static_cast<uint32_t>(8 * ks);
@@ -424,20 +436,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
               umma_tf32_ts(dh, a, bh, kIdesc, 1u);           // hi*hi
             }
           }
-#else
-          for (int ks = kstep; ks < TC_BK / 8; ks += TC_ISSUERS) {
-            const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
-            const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
-            const uint32_t a0 = tmem_acc + 256u + tstage * 128u + static_cast<uint32_t>(8 * ks), a1 = a0 + 64u;
-            const uint32_t d0 = tmem_acc, d1 = tmem_acc + 128u;
-            umma_tf32_ts(d0, a0 + 32u, bh, kIdesc, 1u);     // lo*hi
-            umma_tf32_ts(d1, a1 + 32u, bh, kIdesc, 1u);
-            umma_tf32_ts(d0, a0, bl, kIdesc, 1u);           // hi*lo
-            umma_tf32_ts(d1, a1, bl, kIdesc, 1u);
-            umma_tf32_ts(d0, a0, bh, kIdesc, 1u);           // hi*hi
-            umma_tf32_ts(d1, a1, bh, kIdesc, 1u);
-          }
-#endif
           umma_commit(smem_u32(&bar_mma[tstage]));
           if (((c + 1) % kFlushChunks == 0) || (c == nchunks - 1)) umma_commit(smem_u32(&bar_epoch));
           // weights two chunks ahead: that B stage was last read by round-2, and all of round-2's MMAs are known to
@@ -465,8 +463,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         float* yr = d.y + static_cast<long long>(m) * d.ldy;
         const bool vec_ok = (d.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0);
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          const int co = n0 + my_ch * 64 + j;
+        for (int j = 0; j < ACC; j += 4) {
+          const int co = n0 + my_ch * ACC + j;
           if (co < d.cout) {
             float4 o;
             o.x = activate(acc[j] + (d.bias ? __ldg(d.bias + min(co, d.cout - 1)) : 0.f), d.act, d.act_param);
@@ -498,21 +496,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   }
 }
 
-// w (Cout, Cin, taps) fp32 -> per (n-tile, chunk) smem image [tf32 hi: 128 x 32 | tf32 lo: 128 x 32], K-major,
+// w (Cout, Cin, taps) fp32 -> per (n-tile, chunk) smem image [tf32 hi: BN x 32 | tf32 lo: BN x 32], K-major,
 // 128B-swizzled.  Chunk order = the kernel's: tap-major, then source-0 channel chunks, then source-1 chunks.
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int c0, int c1,
-                                      int taps, long long total) {
+                                      int taps, int BN, long long total) {
   const int nch0 = (c0 + TC_BK - 1) / TC_BK, nch1 = (c1 + TC_BK - 1) / TC_BK;
   const int per_tap = nch0 + nch1;
   const int nchunks = taps * per_tap;
   const int Cin = c0 + c1;
-  const long long tile_floats = static_cast<long long>(TC_BN) * TC_BK;
+  const long long tile_floats = static_cast<long long>(BN) * TC_BK;
   const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += step) {
     // i indexes LOGICAL (nt, chunk, hilo, n, kk); the store address applies the swizzle
     long long t = i;
     const int kk = static_cast<int>(t % TC_BK); t /= TC_BK;
-    const int n = static_cast<int>(t % TC_BN); t /= TC_BN;
+    const int n = static_cast<int>(t % BN); t /= BN;
     const int hilo = static_cast<int>(t % 2); t /= 2;
     const int c = static_cast<int>(t % nchunks);
     const int nt = static_cast<int>(t / nchunks);
@@ -521,7 +519,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
     const bool src1 = rr >= nch0;
     const int ci_local = (src1 ? rr - nch0 : rr) * TC_BK + kk;
     const int csrc = src1 ? c1 : c0;
-    const int co = nt * TC_BN + n;
+    const int co = nt * BN + n;
     float v = 0.f;
     if (ci_local < csrc && co < Cout) {
       const int ci = (src1 ? c0 : 0) + ci_local;
@@ -535,21 +533,36 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
   }
 }
 
+static int tc_tile_n(int cout) { return cout >= 96 ? 128 : (cout >= 48 ? 64 : 32); }
+
+template <int BN>
+static int launch_tc(const wmd_conv_desc& d, cudaStream_t stream) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev]) {
+    int rc = record(cudaFuncSetAttribute(conv_rows_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::SMEM)));
+    if (rc != WMD_OK) return rc;
+    attr_done[dev] = true;
+  }
+  const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN);
+  const long long cap = sm_count();
+  const int grid = static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
+  conv_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w);
+  return launched();
+}
+
 }  // namespace wmd
 
-
-#ifdef WMD_TC_DEBUG
-extern "C" int wmd_debug_read(unsigned int* host) {
-  return static_cast<int>(cudaMemcpyFromSymbol(host, wmd::g_dbg, sizeof(unsigned int) * 4));
-}
-#endif
-
-extern "C" int wmd_conv_tc_tile_n(int cout) { (void)cout; return wmd::TC_BN; }
+extern "C" int wmd_conv_tc_tile_n(int cout) { return wmd::tc_tile_n(cout); }
 
 extern "C" size_t wmd_conv_tc_weight_floats(int cout, int c0, int c1, int taps) {
   using namespace wmd;
+  const int bn = tc_tile_n(cout);
   const int nchunks = taps * ((c0 + TC_BK - 1) / TC_BK + (c1 + TC_BK - 1) / TC_BK);
-  return static_cast<size_t>(ceil_div(cout, TC_BN)) * nchunks * 2 * TC_BN * TC_BK;
+  return static_cast<size_t>(ceil_div(cout, bn)) * nchunks * 2 * bn * TC_BK;
 }
 
 extern "C" int wmd_pack_conv_weight_tc_f32(const float* w, float* packed, int Cout, int c0, int c1, int taps,
@@ -558,7 +571,8 @@ extern "C" int wmd_pack_conv_weight_tc_f32(const float* w, float* packed, int Co
   WMD_REQUIRE(w && packed, WMD_ERR_ARG);
   WMD_REQUIRE(Cout > 0 && c0 > 0 && c1 >= 0 && (taps == 1 || taps == 9), WMD_ERR_SHAPE);
   const long long total = static_cast<long long>(wmd_conv_tc_weight_floats(Cout, c0, c1, taps));
-  pack_weight_tc_kernel<<<stride_grid(total, 256), 256, 0, as_stream(stream)>>>(w, packed, Cout, c0, c1, taps, total);
+  pack_weight_tc_kernel<<<stride_grid(total, 256), 256, 0, as_stream(stream)>>>(w, packed, Cout, c0, c1, taps,
+                                                                               tc_tile_n(Cout), total);
   return launched();
 }
 
@@ -588,18 +602,9 @@ extern "C" int wmd_conv_rows_tc_f32(const wmd_conv_desc* dp, wmd_stream_t stream
                   static_cast<long long>(d.N) * d.H * d.W * (d.ld1 / 4) < (1ll << 32),
               WMD_ERR_UNSUPPORTED);
   if (d.max_rows == 0) return WMD_OK;
-  static bool attr_done[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
-    int rc = record(cudaFuncSetAttribute(conv_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(TC_SMEM)));
-    if (rc != WMD_OK) return rc;
-    attr_done[dev] = true;
+  switch (tc_tile_n(d.cout)) {
+    case 128: return launch_tc<128>(d, as_stream(stream));
+    case 64: return launch_tc<64>(d, as_stream(stream));
+    default: return launch_tc<32>(d, as_stream(stream));
   }
-  const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, TC_BN);
-  const long long cap = sm_count();
-  const int grid = static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
-  conv_rows_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(d, d.w);
-  return launched();
 }

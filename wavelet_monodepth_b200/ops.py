@@ -265,14 +265,15 @@ class PackedW:
         self.data, self.kind, self.taps, self.c0, self.c1, self.cout = data, kind, taps, c0, c1, cout
 
 
-TC_MIN_COUT = 128     # the tcgen05 tile is 256 x 128: narrower outputs waste the tensor pipe, the FMA tiles win
+TC_MIN_K = 128        # shallower reductions (1x1 heads of the fine levels) do not amortise the tile prologue
+TC_MIN_COUT = 32      # tcgen05 tiles are 256 x {128, 64, 32}; below that the FMA tiles / head kernel take over
 
 
 def default_conv_kind():
     """Engine used when a caller does not ask for one: env WMD_CONV_IMPL = auto | simt | tc.
 
-    auto (default): tcgen05 3xTF32 for cout >= 128 (the layers that carry ~85 % of the decoder's FLOPs),
-    fp32 FMA tiles below."""
+    auto (default): tcgen05 3xTF32 for cout >= 32 (every upconv / 1x1 head stage of the decoders), fp32 FMA
+    tiles below."""
     import os
     return os.environ.get("WMD_CONV_IMPL", "auto")
 
@@ -289,7 +290,7 @@ def pack_weight(weight, c1=0, kind=None):
     taps = wt.shape[2] * wt.shape[3]
     c0 = cin - c1
     if kind == "auto":
-        kind = "tc" if cout >= TC_MIN_COUT else "simt"
+        kind = "tc" if (cout >= TC_MIN_COUT and taps * cin >= TC_MIN_K) else "simt"
     if kind == "tc":
         nfl = lib.wmd_conv_tc_weight_floats(cout, c0, c1, taps)
         packed = torch.empty((nfl,), dtype=_f32, device=wt.device)
