@@ -373,6 +373,19 @@ def run_native(args, rank, world, local_rank):
     ops_per_frame = out["total_ops"] / n_local
     value = n_global * args.steps / (ms * 1e-3)
 
+    # ---- 1b. same step with the features handed over channels_last (what a channels_last cuDNN encoder leaves):
+    # the decoder then uses them in place and the five NCHW->rows transposes disappear
+    resident_cl = [f.contiguous(memory_format=torch.channels_last) for f in resident]
+
+    def step_cl():
+        o = dec(resident_cl, THRESH)
+        if world > 1:
+            shard.all_gather_batch(o[("disp", 0)], n_global)
+
+    ms_cl = time_device(step_cl, args.steps, 2, dist, world)
+    value_cl = n_global * args.steps / (ms_cl * 1e-3)
+    del resident_cl
+
     # ---- 2. end to end: host features -> H2D (copy stream, double buffered) -> decode -> D2H of disp0
     copy_stream = torch.cuda.Stream()
     bufs = [[torch.empty_like(f, device=dev) for f in host] for _ in range(2)]
@@ -468,6 +481,8 @@ def run_native(args, rank, world, local_rank):
                 "timed_region": "decoder forward on NCHW fp32 features resident in HBM, incl. layout transposes, "
                                 "mask/compaction, the total_ops count read-back and (N>1) the all-gather",
             },
+            "value_channels_last": {"value": round(value_cl, 1), "unit": UNIT, "ms_per_step": round(ms_cl / args.steps, 3),
+                                    "note": "same step, encoder features in torch.channels_last: used zero-copy, no layout transposes"},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(e2e_ms / args.steps, 3),
                     "note": "pinned host features; H2D double-buffered on a copy stream; PCIe-bound"},

@@ -7,25 +7,49 @@ namespace wmd {
 constexpr int kTT = 32;
 
 // src (N, C, HW) -> dst (N, HW, ld); columns C..ld-1 zero-filled.
+// Tile = 32 channels x 128 pixels.  Read side: a warp streams 128 pixels of one channel as four coalesced 128-byte
+// requests; write side: 8 lanes cover the 32 channels of one pixel as float4 (one full 128-byte
+// line per pixel).  The 129-float row pitch makes the transposed shared-memory reads conflict-free.
+constexpr int kTP = 128;   // pixels per tile
 __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                            int C, long long HW, int ld) {
-  __shared__ float tile[kTT][kTT + 1];
+  __shared__ float tile[kTT][kTP + 1];
   const int n = blockIdx.z;
-  const long long p0 = static_cast<long long>(blockIdx.x) * kTT;
+  const long long p0 = static_cast<long long>(blockIdx.x) * kTP;
   const int c0 = blockIdx.y * kTT;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* s = src + static_cast<long long>(n) * C * HW;
   float* d = dst + static_cast<long long>(n) * HW * ld;
-  for (int r = ty; r < kTT; r += 8) {
+#pragma unroll
+  for (int r = warp; r < kTT; r += 8) {
     const int c = c0 + r;
-    const long long p = p0 + tx;
-    tile[r][tx] = (c < C && p < HW) ? __ldg(s + static_cast<long long>(c) * HW + p) : 0.f;
+    const float* row = s + static_cast<long long>(c) * HW;
+#pragma unroll
+    for (int j = 0; j < kTP / 32; ++j) {          // four fully coalesced 128-byte requests per channel row
+      const long long p = p0 + lane + 32 * j;
+      tile[r][lane + 32 * j] = (c < C && p < HW) ? __ldg(row + p) : 0.f;
+    }
   }
   __syncthreads();
-  for (int r = ty; r < kTT; r += 8) {
-    const long long p = p0 + r;
-    const int c = c0 + tx;
-    if (p < HW && c < ld) d[p * ld + c] = tile[tx][r];
+  const int q = lane & 7;                        // channel quad of this lane
+  const bool vec_out = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d) & 15) == 0);
+#pragma unroll
+  for (int it = 0; it < kTP / 32; ++it) {
+    const int pl = it * 32 + warp * 4 + (lane >> 3);          // pixel within the tile
+    const long long p = p0 + pl;
+    const int c = c0 + 4 * q;
+    if (p < HW && c < ld) {
+      const float4 o = make_float4(tile[4 * q][pl], tile[4 * q + 1][pl], tile[4 * q + 2][pl], tile[4 * q + 3][pl]);
+      float* out = d + p * ld + c;
+      if (vec_out && c + 3 < ld) {
+        *reinterpret_cast<float4*>(out) = o;
+      } else {
+        out[0] = o.x;
+        if (c + 1 < ld) out[1] = o.y;
+        if (c + 2 < ld) out[2] = o.z;
+        if (c + 3 < ld) out[3] = o.w;
+      }
+    }
   }
 }
 
@@ -148,7 +172,7 @@ extern "C" int wmd_nchw_to_rows_f32(const float* src, float* dst, int N, int C, 
   WMD_REQUIRE(src && dst, WMD_ERR_ARG);
   WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
   if (N == 0) return WMD_OK;
-  dim3 grid(ceil_div(HW, kTT), ceil_div(ld, kTT), N);
+  dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
   WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
   nchw_to_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, HW, ld);
   return launched();
