@@ -194,6 +194,16 @@ typedef struct wmd_head_desc {
 
 int wmd_head_conv3x3_f32(const wmd_head_desc* d, wmd_stream_t stream);
 
+/* Factored form of the same stage (what the decoders use for the +/- heads): the per-tap products
+ * z[row, tap*groups + g] = t[row, :] . w_g[:, tap] are computed once per active input row by wmd_conv_rows_*_f32
+ * (taps = 1, cout = 9*groups); this entry point gathers and sums the nine taps per output pixel,
+ *   s_g = bias[g] + sum_tap z[map(p + tap), tap*groups + g],
+ * and scatters  out[n, j, y, x] = scale * (act(s_j) - act(s_{cout+j}))  (dual, groups = 2*cout)  or  scale * act(s_j)
+ * (groups = cout) into the dense NCHW tensor (zero-filled by the caller when pixels != NULL).  groups in {1,2,3,4,6,8}. */
+int wmd_head_gather_f32(const float* z, int ldz, int groups, const int32_t* map, const float* bias, float scale, int act,
+                        int dual, int pad_mode, const int32_t* pixels, const int32_t* count, int max_rows, float* out,
+                        int cout, int N, int H, int W, wmd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

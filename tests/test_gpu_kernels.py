@@ -305,3 +305,26 @@ def test_head_conv_vs_oracle(c, cout, dual):
                              act=ACT_SIGMOID, pad=PAD_REFLECT, pixels=pix, count=off[n:], **kw)
     assert rel_err(got_s, want * mask.cpu().float()) <= REL_TOL
     assert bool((got_s.cpu()[mask.cpu().expand(-1, cout, -1, -1) == 0] == 0).all())
+
+
+@pytest.mark.parametrize("c", [32, 128])
+def test_factored_head_vs_torch(c, kind):
+    """Tap-product GEMM + gather-sum == conv3x3(reflect) -> sigmoid difference of the +/- heads."""
+    n, h, w = 2, 9, 14
+    t = rnd(n, 2 * c, h, w, seed=70)
+    wa, ba = rnd(3, c, 3, 3, seed=71, lo=-0.3, hi=0.3), rnd(3, seed=72)
+    wb, bb = rnd(3, c, 3, 3, seed=73, lo=-0.3, hi=0.3), rnd(3, seed=74)
+    want = 2.0 * (torch.sigmoid(F.conv2d(F.pad(t[:, :c], (1, 1, 1, 1), mode="reflect"), wa, ba)) -
+                  torch.sigmoid(F.conv2d(F.pad(t[:, c:], (1, 1, 1, 1), mode="reflect"), wb, bb)))
+    rows = ops.nchw_to_rows(t.to(DEV))
+    wz = ops.pack_weight(ops.head_tap_weight([wa.to(DEV), wb.to(DEV)], [0, c], 2 * c), kind=kind)
+    z = ops.conv_rows(rows, 2 * c, wz, None, 54, n, h, w, taps=1)
+    bias = torch.cat([ba, bb]).to(DEV)
+    got = ops.head_gather(z, 6, bias, n, h, w, 3, scale=2.0, act=ACT_SIGMOID, dual=True, pad=PAD_REFLECT)
+    assert rel_err(got, want) <= REL_TOL
+    rs = np.random.RandomState(75)
+    mask = torch.from_numpy((rs.uniform(size=(n, 1, h, w)) < 0.3).astype(np.uint8)).to(DEV)
+    _, pix, off = ops.compact(mask, want_idxmap=False)
+    got_s = ops.head_gather(z, 6, bias, n, h, w, 3, scale=2.0, act=ACT_SIGMOID, dual=True, pad=PAD_REFLECT,
+                            pixels=pix, count=off[n:])
+    assert rel_err(got_s, want * mask.cpu().float()) <= REL_TOL

@@ -109,7 +109,103 @@ static int launch_head(const wmd_head_desc& d, cudaStream_t stream) {
   return launched();
 }
 
+// ---- factored form of the same 3x3 stage -------------------------------------------------------------------------
+// conv3x3 over a gathered neighbourhood = sum over taps of (row . W[tap]).  The row . W[tap] products for all 9 taps
+// do not depend on which pixel asks for them, so they are computed ONCE per active input row by the tensor-core
+// GEMM (Z = T x Wz, Wz = [tap][group] columns, wmd_conv_rows_* with taps = 1), and this kernel only gathers and adds
+// 9 x G floats per output pixel (G = 6 for a +/- pair of 3-channel heads) instead of 9 x 2C: 10-80x less gather
+// traffic.  One thread per output pixel; consecutive threads take consecutive active pixels, i.e. neighbours in
+// x, so the nine Z rows they touch are mostly adjacent in memory.
+template <int G>
+__global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ z, int ldz,
+                                                          const int32_t* __restrict__ map, const float* __restrict__ bias,
+                                                          float scale, int act, int dual, int pad_mode,
+                                                          const int32_t* __restrict__ pixels, const int32_t* __restrict__ count,
+                                                          int max_rows, float* __restrict__ out, int cout, int N, int H, int W) {
+  const long long HW = static_cast<long long>(H) * W;
+  const int total_px = static_cast<int>(static_cast<long long>(N) * HW);
+  int rows = pixels ? *count : total_px;
+  rows = min(rows, max_rows);
+  float b[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) b[g] = bias ? __ldg(bias + g) : 0.f;
+  const int step = gridDim.x * blockDim.x;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < rows; m += step) {
+    const int p = pixels ? pixels[m] : m;
+    const int n = static_cast<int>(p / HW);
+    const int rem = static_cast<int>(p - n * HW);
+    const int y = rem / W, x = rem - y * W;
+    float s[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) s[g] = b[g];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      int qy = y + tap / 3 - 1, qx = x + tap % 3 - 1;
+      bool ok = pad_coord(qy, H, pad_mode);
+      ok = pad_coord(qx, W, pad_mode) && ok;
+      if (!ok) continue;
+      const int q = (n * H + qy) * W + qx;
+      const int row = map ? map[q] : q;
+      if (row < 0) continue;
+      const float* zr = z + static_cast<long long>(row) * ldz + tap * G;
+      if (G % 2 == 0 && (ldz % 2) == 0) {
+#pragma unroll
+        for (int g = 0; g < G; g += 2) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(zr + g));
+          s[g] += v.x;
+          s[g + 1] += v.y;
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) s[g] += __ldg(zr + g);
+      }
+    }
+    if (dual) {
+#pragma unroll
+      for (int j = 0; j < G / 2; ++j)
+        if (j < cout)
+          out[(static_cast<long long>(n) * cout + j) * HW + rem] =
+              scale * (activate(s[j], act, 0.f) - activate(s[G / 2 + j], act, 0.f));
+    } else {
+#pragma unroll
+      for (int j = 0; j < G; ++j)
+        if (j < cout) out[(static_cast<long long>(n) * cout + j) * HW + rem] = scale * activate(s[j], act, 0.f);
+    }
+  }
+}
+
 }  // namespace wmd
+
+extern "C" int wmd_head_gather_f32(const float* z, int ldz, int groups, const int32_t* map, const float* bias, float scale,
+                                   int act, int dual, int pad_mode, const int32_t* pixels, const int32_t* count,
+                                   int max_rows, float* out, int cout, int N, int H, int W, wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(z && out, WMD_ERR_ARG);
+  WMD_REQUIRE((pixels == nullptr) == (count == nullptr), WMD_ERR_ARG);
+  WMD_REQUIRE(N > 0 && H > 0 && W > 0 && max_rows >= 0 && ldz >= 9 * groups, WMD_ERR_SHAPE);
+  WMD_REQUIRE(static_cast<long long>(N) * H * W < (1ll << 31), WMD_ERR_SHAPE);
+  WMD_REQUIRE(pad_mode >= WMD_PAD_ZERO && pad_mode <= WMD_PAD_REPLICATE, WMD_ERR_ARG);
+  WMD_REQUIRE(act >= WMD_ACT_NONE && act <= WMD_ACT_SIGMOID && act != WMD_ACT_LRELU, WMD_ERR_ARG);
+  WMD_REQUIRE(dual ? (groups == 2 * cout) : (groups == cout), WMD_ERR_SHAPE);
+  if (pad_mode == WMD_PAD_REFLECT) WMD_REQUIRE(H >= 2 && W >= 2, WMD_ERR_SHAPE);
+  if (max_rows == 0) return WMD_OK;
+  const int grid = stride_grid(max_rows, 256, 8);
+  cudaStream_t st = as_stream(stream);
+#define WMD_LAUNCH_GATHER(GG)                                                                                         \
+  head_gather_kernel<GG><<<grid, 256, 0, st>>>(z, ldz, map, bias, scale, act, dual, pad_mode, pixels, count, max_rows, \
+                                               out, cout, N, H, W)
+  switch (groups) {
+    case 1: WMD_LAUNCH_GATHER(1); break;
+    case 2: WMD_LAUNCH_GATHER(2); break;
+    case 3: WMD_LAUNCH_GATHER(3); break;
+    case 4: WMD_LAUNCH_GATHER(4); break;
+    case 6: WMD_LAUNCH_GATHER(6); break;
+    case 8: WMD_LAUNCH_GATHER(8); break;
+    default: return WMD_ERR_UNSUPPORTED;
+  }
+#undef WMD_LAUNCH_GATHER
+  return launched();
+}
 
 extern "C" int wmd_head_conv3x3_f32(const wmd_head_desc* dp, wmd_stream_t stream) {
   using namespace wmd;

@@ -148,6 +148,16 @@ class _WaveDecoderBase(nn.Module):
             run += c.weight.shape[0]
         return packed, bias, offs, run
 
+    def _head_taps(self, i, offs, ctot):
+        """Factored +/- 3x3 stage: packed (54, ctot) tap-product weight and the 6 biases [+ | -]."""
+        cp, cn = self.convs[("waveconv", i, 1)][2].conv, self.convs[("waveconv", i, -1)][2].conv
+        kind = ops.default_conv_kind()
+        wz = self._packs.get(("headtaps", i, kind), [cp.weight, cn.weight],
+                             lambda: ops.pack_weight(ops.head_tap_weight([cp.weight, cn.weight], [offs[1], offs[-1]], ctot)))
+        bz = self._packs.get(("headtapsb", i), [cp.bias, cn.bias],
+                             lambda: torch.cat([cp.bias.detach(), cn.bias.detach()]).contiguous())
+        return wz, bz
+
     def _head_3x3(self, i, j):
         conv = self.convs[("waveconv", i, j)][2].conv
         return self._packs.get(("head3x3", i, j), [conv.weight], lambda: ops.pack_head_weight(conv.weight)), conv.bias.detach()
@@ -221,10 +231,14 @@ class _WaveDecoderBase(nn.Module):
                 wl, bl = self._head_3x3(i, 0)
                 yl = ops.head_conv3x3(t, c // 4, offs[0], wl, bl, n, 2 * h, 2 * w, 1, scale=float(2 ** i),
                                       act=ACT_SIGMOID, pad=PAD_REFLECT)
-            wpos, bpos = self._head_3x3(i, 1)
-            wneg, bneg = self._head_3x3(i, -1)
-            yh = ops.head_conv3x3(t, c, offs[1], wpos, bpos, n, 2 * h, 2 * w, 3, scale=float(2 ** (i - 1)),
-                                  act=ACT_SIGMOID, pad=PAD_REFLECT, off_b=offs[-1], wb=wneg, bb=bneg, **head_kw)
+            # +/- heads, factored: per-row tap products on the GEMM engine, then a 9 x 6 float gather-sum per pixel
+            wz, bz = self._head_taps(i, offs, c1x1)
+            if sparse:
+                z = ops.conv_rows(t, c1x1, wz, None, 54, n, 2 * h, 2 * w, taps=1, pixels=pix4, count=off4[n:], m_in0=off4[n:])
+            else:
+                z = ops.conv_rows(t, c1x1, wz, None, 54, n, 2 * h, 2 * w, taps=1)
+            yh = ops.head_gather(z, 6, bz, n, 2 * h, 2 * w, 3, scale=float(2 ** (i - 1)), act=ACT_SIGMOID, dual=True,
+                                 pad=PAD_REFLECT, **head_kw)
             out[("wavelets", i - 1, "LL")] = yl
             out[("wavelets", i - 1, "LH")] = yh[:, 0:1]
             out[("wavelets", i - 1, "HL")] = yh[:, 1:2]

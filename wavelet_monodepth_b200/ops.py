@@ -377,3 +377,34 @@ def pack_head_weight(weight):
     rc = lib.wmd_pack_conv_weight_f32(_lib.ptr(wt), _lib.ptr(packed), cout, cin, 9, cout, _lib.stream_ptr())
     _lib.check(rc, "wmd_pack_conv_weight_f32")
     return packed
+
+
+def head_tap_weight(w_list, offsets, ctot):
+    """1x1-conv weight (9*G, ctot, 1, 1) of the factored 3x3 head stage: row tap*G + g = head-group g's tap-th filter.
+
+    w_list: 3x3 weights [(co_k, c_k, 3, 3)] of the heads; offsets: channel offset of each head's input inside the
+    ctot-wide T row.  Groups are the heads' output channels concatenated in order (G = sum co_k)."""
+    g_total = sum(int(w.shape[0]) for w in w_list)
+    out = torch.zeros((9, g_total, ctot), dtype=_f32, device=w_list[0].device)
+    g0 = 0
+    for w, off in zip(w_list, offsets):
+        co, c = int(w.shape[0]), int(w.shape[1])
+        out[:, g0:g0 + co, off:off + c] = w.detach().permute(2, 3, 0, 1).reshape(9, co, c)
+        g0 += co
+    return out.reshape(9 * g_total, ctot, 1, 1)
+
+
+def head_gather(z, groups, bias, n, h, w, cout, scale=1.0, act=ACT_NONE, dual=False, pad=PAD_REFLECT, idxmap=None,
+                pixels=None, count=None, max_rows=None, out=None):
+    """Sum the nine per-tap products of z (rows x >= 9*groups) around every output pixel -> dense (N,cout,H,W)."""
+    lib = _lib.load()
+    total = n * h * w
+    max_rows = total if max_rows is None else int(max_rows)
+    if out is None:
+        out = (torch.zeros if pixels is not None else torch.empty)((n, cout, h, w), dtype=_f32, device=z.device)
+    with _prof('head_gather', lambda: dict(n=n, h=h, w=w, groups=groups, cout=cout, count=count, max_rows=max_rows)):
+        rc = lib.wmd_head_gather_f32(_lib.ptr(z, _f32), z.shape[1], groups, _lib.ptr(idxmap, _i32), _lib.ptr(bias, _f32),
+                                     float(scale), act, int(bool(dual)), pad, _lib.ptr(pixels, _i32), _lib.ptr(count, _i32),
+                                     max_rows, _lib.ptr(out, _f32), cout, n, h, w, _lib.stream_ptr())
+    _lib.check(rc, "wmd_head_gather_f32")
+    return out
