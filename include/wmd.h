@@ -170,6 +170,11 @@ int wmd_conv_tc_tile_n(int cout);
 size_t wmd_conv_tc_weight_floats(int cout, int c0, int c1, int taps);
 int wmd_pack_conv_weight_tc_f32(const float* w, float* packed, int Cout, int c0, int c1, int taps, wmd_stream_t stream);
 int wmd_conv_rows_tc_f32(const wmd_conv_desc* d, wmd_stream_t stream);
+/* Same, with the reduction split `splits` ways across CTAs (split-K): layers with few output tiles then fill all
+ * SMs.  Partial sums go to `ws` (wmd_conv_tc_splitk_ws_bytes) and are summed in a fixed order, biased and
+ * activated by a second small kernel, so results stay deterministic.  splits = 1 is wmd_conv_rows_tc_f32. */
+size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits);
+int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* d, int splits, void* ws, size_t ws_bytes, wmd_stream_t stream);
 
 /* ---------------------------------------------------------------- coefficient heads (few output channels)
  * The 3x3 stage of the wavelet heads (depth_decoder.py:104-120,126-136,242-290; NYU wave convs

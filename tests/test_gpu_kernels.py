@@ -328,3 +328,24 @@ def test_factored_head_vs_torch(c, kind):
     got_s = ops.head_gather(z, 6, bias, n, h, w, 3, scale=2.0, act=ACT_SIGMOID, dual=True, pad=PAD_REFLECT,
                             pixels=pix, count=off[n:])
     assert rel_err(got_s, want * mask.cpu().float()) <= REL_TOL
+
+
+@pytest.mark.parametrize("splits", [2, 3, 4])
+def test_tc_split_k_vs_torch(splits):
+    """Split-K work items + fixed-order reduce pass give the same convolution (and are deterministic)."""
+    n, cin, cout, h, w = 2, 160, 128, 9, 13
+    x, wt, b = rnd(n, cin, h, w, seed=80), rnd(cout, cin, 3, 3, seed=81, lo=-0.1, hi=0.1), rnd(cout, seed=82)
+    want = _torch_conv(x, wt, b, PAD_REFLECT, ACT_ELU)
+    rows, wp = ops.nchw_to_rows(x.to(DEV)), ops.pack_weight(wt.to(DEV), kind="tc")
+    y = ops.conv_rows(rows, cin, wp, b.to(DEV), cout, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, splits=splits)
+    assert rel_err(ops.rows_to_nchw(y, n, cout, h, w), want) <= REL_TOL
+    y2 = ops.conv_rows(rows, cin, wp, b.to(DEV), cout, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, splits=splits)
+    assert torch.equal(y, y2)
+    # sparse list + split-K
+    rs = np.random.RandomState(83)
+    mask = torch.from_numpy((rs.uniform(size=(n, 1, h, w)) < 0.4).astype(np.uint8)).to(DEV)
+    _, pix, off = ops.compact(mask, want_idxmap=False)
+    ys = ops.conv_rows(rows, cin, wp, b.to(DEV), cout, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, pixels=pix, count=off[n:],
+                       splits=splits)
+    got = ops.scatter_rows(ys, cout, pix, off[n:], n, h, w)
+    assert rel_err(got, want * mask.cpu().float()) <= REL_TOL

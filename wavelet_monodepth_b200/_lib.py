@@ -78,6 +78,8 @@ SIGNATURES = {
     "wmd_conv_tc_weight_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "wmd_pack_conv_weight_tc_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "wmd_conv_rows_tc_f32": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "wmd_conv_tc_splitk_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "wmd_conv_rows_tc_splitk_f32": (c_int, [POINTER(ConvDesc), c_int, c_void_p, c_size_t, c_void_p]),
     "wmd_head_conv3x3_f32": (c_int, [POINTER(HeadDesc), c_void_p]),
     "wmd_head_gather_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

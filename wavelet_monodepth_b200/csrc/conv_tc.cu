@@ -160,7 +160,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_conv_desc d, const float* __restrict__ wtc) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_conv_desc d, const float* __restrict__ wtc,
+                                                                     const int splits, float* __restrict__ partial) {
   using Cfg = TcCfg<BN>;
   constexpr int TC_B_TILE = Cfg::B_TILE;
   constexpr int TC_ISSUERS = Cfg::ISSUERS;
@@ -235,7 +236,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   __syncthreads();
   tc_fence_after();
 
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  // work item = (output tile, K split): with split-K the chunk range [cb, ce) of the reduction is handled here and
+  // the raw partial sums go to a workspace (summed, biased and activated by splitk_reduce_kernel) - more, shorter
+  // items fill the 148 SMs evenly when a layer has few tiles
+  const long long items = tiles * splits;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long tile = item / splits;
+    const int ks = static_cast<int>(item - tile * splits);
+    const int cb = static_cast<int>(static_cast<long long>(ks) * nchunks / splits);
+    const int ce = static_cast<int>(static_cast<long long>(ks + 1) * nchunks / splits);
+    const int len = ce - cb;
     const int m0 = static_cast<int>(tile / n_tiles) * TC_BM;
     const int nt = static_cast<int>(tile % n_tiles);
     const int n0 = nt * BN;
@@ -319,10 +329,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         }
       };
       // raw fp32 A tile of chunk c -> shared A stage c&1 (128B-swizzled rows); 2048 pieces over 384 threads
-      auto load_a = [&](int c) {
+      auto load_a = [&](int c, int st) {
         const float4* xq; int cleft;
         const uint32_t* tab = chunk_src(c, xq, cleft);
-        unsigned char* sA = sA_base + (c & 1) * TC_A_TILE;
+        unsigned char* sA = sA_base + st * TC_A_TILE;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           const int p = tid + i * TC_PROD_THREADS;
@@ -337,19 +347,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         }
       };
 
-      for (int c = 1; c <= kPrefetchAhead && c < nchunks; ++c) prefetch_chunk(c);
-      load_a(0);
+      for (int c = 1; c <= kPrefetchAhead && c < len; ++c) prefetch_chunk(cb + c);
+      load_a(cb, 0);
       cp_async_commit();
 
       const int wt = warp >> 2;                      // 0..2: which of the quarter's three producer warps
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
         const uint32_t tstage = round & 1;
         cp_async_wait<0>();
         producer_barrier();                          // raw A tile of chunk c complete; split reads of chunk c-1 done
-        if (c + 1 < nchunks) {
-          load_a(c + 1);
-          if (c + 1 + kPrefetchAhead < nchunks) prefetch_chunk(c + 1 + kPrefetchAhead);
+        if (c + 1 < len) {
+          load_a(cb + c + 1, (c + 1) & 1);
+          if (c + 1 + kPrefetchAhead < len) prefetch_chunk(cb + c + 1 + kPrefetchAhead);
         }
         cp_async_commit();
         if ((c % kFlushChunks) == 0 && c > 0) {      // epoch boundary: everybody drains before the next epoch starts
@@ -392,19 +402,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_asplit[tstage]));
-        if (((c + 1) % kFlushChunks == 0) || (c == nchunks - 1)) epochs += 1;
+        if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
       }
     } else {
       // =================================================================================== issuers
       const int kstep = warp - TC_PROD_WARPS;        // this issuer's k-step inside every chunk
       if (kstep == 0 && lane == 0) {
-        bulk_g2s(smem_u32(sB_base + (round0 % TC_B_STAGES) * 2 * TC_B_TILE), wtile, 2 * TC_B_TILE,
+        const unsigned char* w0 = wtile + static_cast<long long>(cb) * (2 * TC_B_TILE);
+        bulk_g2s(smem_u32(sB_base + (round0 % TC_B_STAGES) * 2 * TC_B_TILE), w0, 2 * TC_B_TILE,
                  smem_u32(&bar_b[round0 % TC_B_STAGES]));
-        if (nchunks > 1)
-          bulk_g2s(smem_u32(sB_base + ((round0 + 1) % TC_B_STAGES) * 2 * TC_B_TILE), wtile + 2 * TC_B_TILE, 2 * TC_B_TILE,
+        if (len > 1)
+          bulk_g2s(smem_u32(sB_base + ((round0 + 1) % TC_B_STAGES) * 2 * TC_B_TILE), w0 + 2 * TC_B_TILE, 2 * TC_B_TILE,
                    smem_u32(&bar_b[(round0 + 1) % TC_B_STAGES]));
       }
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
         const uint32_t tstage = round & 1;
         const uint32_t bs = round % TC_B_STAGES;
@@ -437,21 +448,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
             }
           }
           umma_commit(smem_u32(&bar_mma[tstage]));
-          if (((c + 1) % kFlushChunks == 0) || (c == nchunks - 1)) umma_commit(smem_u32(&bar_epoch));
+          if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) umma_commit(smem_u32(&bar_epoch));
           // weights two chunks ahead: that B stage was last read by round-2, and all of round-2's MMAs are known to
           // be complete - the producers only stored this chunk's A (bar_asplit, awaited above) after bar_mma(round-2).
           // (Waiting on bar_mma here would alias: this round's own commits may already have flipped its phase.)
-          if (kstep == 0 && c + 2 < nchunks) {
+          if (kstep == 0 && c + 2 < len) {
             const uint32_t ns = (round + 2) % TC_B_STAGES;
-            bulk_g2s(smem_u32(sB_base + ns * 2 * TC_B_TILE), wtile + static_cast<long long>(c + 2) * (2 * TC_B_TILE),
+            bulk_g2s(smem_u32(sB_base + ns * 2 * TC_B_TILE), wtile + static_cast<long long>(cb + c + 2) * (2 * TC_B_TILE),
                      2 * TC_B_TILE, smem_u32(&bar_b[ns]));
           }
         }
         __syncwarp();
-        if (((c + 1) % kFlushChunks == 0) || (c == nchunks - 1)) epochs += 1;
+        if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
       }
     }
-    mma_rounds = round0 + static_cast<uint32_t>(nchunks);
+    mma_rounds = round0 + static_cast<uint32_t>(len);
 
     // ---- last epoch + epilogue (all 16 warps): bias, activation, one contiguous 256-byte store per thread
     {
@@ -459,7 +470,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       tc_fence_after();
       drain();
       const int m = m0 + my_row;
-      if (m < rows) {
+      if (m < rows && splits > 1) {
+        // raw partial sums of this K split (bias / activation are applied by the reduce pass)
+        float* pr = partial + (static_cast<long long>(ks) * d.max_rows + m) * d.ldy;
+#pragma unroll
+        for (int j = 0; j < ACC; ++j) {
+          const int co = n0 + my_ch * ACC + j;
+          if (co < d.cout) pr[co] = acc[j];
+        }
+      } else if (m < rows) {
         float* yr = d.y + static_cast<long long>(m) * d.ldy;
         const bool vec_ok = (d.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0);
 #pragma unroll
@@ -533,10 +552,28 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
   }
 }
 
+// y[m, co] = act(bias[co] + sum_s partial[s][m][co]) in a fixed order (deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ bias,
+                                     float* __restrict__ y, int ldy, int cout, const int32_t* __restrict__ count,
+                                     int max_rows, int act, float act_param) {
+  const int rows = count ? min(*count, max_rows) : max_rows;
+  const long long total = static_cast<long long>(rows) * cout;
+  const long long slab = static_cast<long long>(max_rows) * ldy;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += step) {
+    const long long m = i / cout;
+    const int co = static_cast<int>(i - m * cout);
+    const long long o = m * ldy + co;
+    float v = bias ? __ldg(bias + co) : 0.f;
+    for (int sidx = 0; sidx < splits; ++sidx) v += __ldg(partial + sidx * slab + o);
+    y[o] = activate(v, act, act_param);
+  }
+}
+
 static int tc_tile_n(int cout) { return cout >= 96 ? 128 : (cout >= 48 ? 64 : 32); }
 
 template <int BN>
-static int launch_tc(const wmd_conv_desc& d, cudaStream_t stream) {
+static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   static bool attr_done[64] = {};
   int dev = 0;
@@ -547,10 +584,15 @@ static int launch_tc(const wmd_conv_desc& d, cudaStream_t stream) {
     if (rc != WMD_OK) return rc;
     attr_done[dev] = true;
   }
-  const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN);
+  const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN) * splits;
   const long long cap = sm_count();
   const int grid = static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
-  conv_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w);
+  conv_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial);
+  int rc = launched();
+  if (rc != WMD_OK || splits == 1) return rc;
+  const long long total = static_cast<long long>(d.max_rows) * d.cout;
+  splitk_reduce_kernel<<<stride_grid(total, 256), 256, 0, stream>>>(partial, splits, d.bias, d.y, d.ldy, d.cout, d.count,
+                                                                  d.max_rows, d.act, d.act_param);
   return launched();
 }
 
@@ -576,9 +618,21 @@ extern "C" int wmd_pack_conv_weight_tc_f32(const float* w, float* packed, int Co
   return launched();
 }
 
+extern "C" size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits) {
+  return splits <= 1 ? 0 : static_cast<size_t>(splits) * static_cast<size_t>(max_rows) * static_cast<size_t>(ldy) * sizeof(float);
+}
+
 extern "C" int wmd_conv_rows_tc_f32(const wmd_conv_desc* dp, wmd_stream_t stream) {
+  return wmd_conv_rows_tc_splitk_f32(dp, 1, nullptr, 0, stream);
+}
+
+extern "C" int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* dp, int splits, void* ws, size_t ws_bytes,
+                                           wmd_stream_t stream) {
   using namespace wmd;
   WMD_REQUIRE(dp, WMD_ERR_ARG);
+  WMD_REQUIRE(splits >= 1 && splits <= 16, WMD_ERR_ARG);
+  WMD_REQUIRE(splits == 1 || (ws != nullptr && ws_bytes >= wmd_conv_tc_splitk_ws_bytes(dp->max_rows, dp->ldy, splits)),
+              WMD_ERR_WORKSPACE);
   wmd_conv_desc d = *dp;
   WMD_REQUIRE(d.x0 && d.w && d.y, WMD_ERR_ARG);
   WMD_REQUIRE(d.taps == 1 || d.taps == 9, WMD_ERR_ARG);
@@ -602,9 +656,14 @@ extern "C" int wmd_conv_rows_tc_f32(const wmd_conv_desc* dp, wmd_stream_t stream
                   static_cast<long long>(d.N) * d.H * d.W * (d.ld1 / 4) < (1ll << 32),
               WMD_ERR_UNSUPPORTED);
   if (d.max_rows == 0) return WMD_OK;
+  {
+    const int nchunks = d.taps * ((d.c0 + TC_BK - 1) / TC_BK + (d.c1 + TC_BK - 1) / TC_BK);
+    if (splits > nchunks) splits = nchunks;      // every split needs at least one chunk
+  }
+  float* partial = static_cast<float*>(ws);
   switch (tc_tile_n(d.cout)) {
-    case 128: return launch_tc<128>(d, as_stream(stream));
-    case 64: return launch_tc<64>(d, as_stream(stream));
-    default: return launch_tc<32>(d, as_stream(stream));
+    case 128: return launch_tc<128>(d, splits, partial, as_stream(stream));
+    case 64: return launch_tc<64>(d, splits, partial, as_stream(stream));
+    default: return launch_tc<32>(d, splits, partial, as_stream(stream));
   }
 }

@@ -33,12 +33,20 @@ class _Scratch:
     def __init__(self):
         self.range_ws = {}
         self.compact_ws = {}
+        self.splitk_ws = {}
 
     def range(self, device, nbytes):
         buf = self.range_ws.get(device)
         if buf is None or buf.numel() < nbytes:
             buf = torch.zeros(max(nbytes, 1 << 16), dtype=_u8, device=device)   # zeroed once; kernel keeps it zero
             self.range_ws[device] = buf
+        return buf
+
+    def splitk(self, device, nbytes):
+        buf = self.splitk_ws.get(device)
+        if buf is None or buf.numel() * 4 < nbytes:
+            buf = torch.empty((nbytes + 3) // 4, dtype=_f32, device=device)
+            self.splitk_ws[device] = buf
         return buf
 
     def compact(self, device, nbytes):
@@ -257,6 +265,33 @@ def scatter_rows(rows, c, pixels, count, n, h, w, max_rows=None, out=None):
     return out
 
 
+_sm_count = {}
+
+
+def tc_splits(max_rows, cout, nchunks, device):
+    """Split-K factor for the tcgen05 engine.
+
+    tiles = ceil(rows/256) * ceil(cout/N) equal work items run on one CTA per SM.  Splitting the reduction only pays
+    when the layer cannot even fill the SMs once (measured: the partial-sum pass and the per-item prologue eat the
+    gain otherwise), e.g. the coarsest level (R50 1024x320 bs32 upconv(4,0): 80 tiles -> 3 splits, 0.78 -> 0.63 ms)
+    and small batches.  Every split keeps >= 8 chunks."""
+    lib = _lib.load()
+    key = str(device)
+    if key not in _sm_count:
+        _sm_count[key] = torch.cuda.get_device_properties(device).multi_processor_count
+    sms = _sm_count[key]
+    bn = lib.wmd_conv_tc_tile_n(cout)
+    tiles = -(-max_rows // 256) * -(-cout // bn)
+    if tiles > 0.75 * sms:
+        return 1
+    best = 1
+    for s in (2, 3, 4):
+        if nchunks // s < 8 or tiles * s > 1.7 * sms:
+            break
+        best = s
+    return best
+
+
 class PackedW:
     """A conv weight packed for one of the two gather-GEMM engines ('simt' fp32 FMA, 'tc' tcgen05 3xTF32)."""
     __slots__ = ("data", "kind", "taps", "c0", "c1", "cout")
@@ -307,7 +342,7 @@ def pack_weight(weight, c1=0, kind=None):
 # --------------------------------------------------------------------------- conv
 def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act=ACT_NONE, act_param=0.0,
               map0=None, shift0=0, x1=None, c1=0, gate=None, pixels=None, count=None, max_rows=None, out=None,
-              m_in0=None, m_in1=None):
+              m_in0=None, m_in1=None, splits=None):
     """Gather-GEMM convolution on pixel-major rows; see wmd_conv_rows_f32 in include/wmd.h.
 
     m_in0 / m_in1: optional active-row counts of the two sources (ints or 1-element device tensors), used only
@@ -336,9 +371,19 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
     d.pixels, d.count, d.max_rows = _lib.ptr(pixels, _i32), _lib.ptr(count, _i32), max_rows
     d.y, d.ldy = _lib.ptr(out, _f32), out.shape[1]
     d.act, d.act_param = act, float(act_param)
-    fn = lib.wmd_conv_rows_tc_f32 if wpacked.kind == "tc" else lib.wmd_conv_rows_f32
-    with _prof('conv_rows', lambda: dict(n=n, h=h, w=w, taps=taps, c0=c0, c1=c1, cout=cout, shift0=shift0, count=count, max_rows=max_rows, m_in0=m_in0, m_in1=m_in1, kind=wpacked.kind)):
-        rc = fn(ctypes.byref(d), _lib.stream_ptr())
+    info = lambda: dict(n=n, h=h, w=w, taps=taps, c0=c0, c1=c1, cout=cout, shift0=shift0, count=count,   # noqa: E731
+                        max_rows=max_rows, m_in0=m_in0, m_in1=m_in1, kind=wpacked.kind)
+    if wpacked.kind == "tc":
+        splits = tc_splits(max_rows, cout, taps * (-(-c0 // 32) + -(-c1 // 32)), dev) if splits is None else splits
+        ws = None
+        if splits > 1:
+            ws = _scratch.splitk(dev, lib.wmd_conv_tc_splitk_ws_bytes(max_rows, out.shape[1], splits))
+        with _prof('conv_rows', info):
+            rc = lib.wmd_conv_rows_tc_splitk_f32(ctypes.byref(d), splits, _lib.ptr(ws), ws.numel() * 4 if ws is not None else 0,
+                                                 _lib.stream_ptr())
+    else:
+        with _prof('conv_rows', info):
+            rc = lib.wmd_conv_rows_f32(ctypes.byref(d), _lib.stream_ptr())
     _lib.check(rc, "wmd_conv_rows_%sf32" % ("tc_" if wpacked.kind == "tc" else ""))
     return out
 
