@@ -64,13 +64,15 @@ def synth_features(wl, n, first_sample, pin):
 
 
 def measured_peaks():
+    """(HBM GB/s, bf16 dense TFLOP/s burst, source)."""
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md 6.65 TB/s, 1.59 PFLOP/s)"
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -135,7 +137,7 @@ def _as_int(v, default):
 
 def account(name, info):
     """(algorithmic bytes, flops) of one launch - SURVEY 8(d) / DESIGN.md 'algorithmic bytes'."""
-    if name == "conv_rows":
+    if name in ("conv_rows", "conv_rows_tc"):
         n, h, w, taps, c0, c1, cout = (info[k] for k in ("n", "h", "w", "taps", "c0", "c1", "cout"))
         total = n * h * w
         m_out = min(_as_int(info["count"], total), info["max_rows"])
@@ -144,6 +146,10 @@ def account(name, info):
         by = 4 * (m0 * c0 + m1 * c1 + m_out * cout) + 4 * (taps * (c0 + c1) * cout + cout)
         by += total if info["count"] is not None else 0                 # 1-byte gate / list traffic
         return by, 2 * taps * (c0 + c1) * cout * m_out
+    if name == "head_gather":
+        n, h, w, g, cout = (info[k] for k in ("n", "h", "w", "groups", "cout"))
+        m = min(_as_int(info["count"], n * h * w), info["max_rows"])
+        return 4 * m * (9 * g + cout) + (n * h * w if info["count"] is not None else 0), 9 * g * m
     if name == "head_conv3x3":
         n, h, w, c, cout = (info[k] for k in ("n", "h", "w", "c", "cout"))
         m = min(_as_int(info["count"], n * h * w), info["max_rows"])
@@ -170,7 +176,7 @@ def account(name, info):
     return 0, 0
 
 
-def roofline_from(records, peak_gbs, peak_src, steps):
+def roofline_from(records, peak_gbs, peak_tf, peak_src, steps):
     agg = {}
     for name, ms, info in records:
         by, fl = account(name, info)
@@ -188,12 +194,27 @@ def roofline_from(records, peak_gbs, peak_src, steps):
             "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 2) if a["ms"] > 0 else 0.0,
         }
     dom = max(agg, key=lambda k: agg[k]["ms"])
-    main = dict(out[dom])
-    main.update(kernel=dom, peak_source=peak_src,
-                note="fp32 SIMT gather-GEMM: arithmetic intensity ~100-400 flop/B puts it on the fp32 FMA roof "
-                     "(%.1f TFLOP/s nominal at max clock), not the HBM roof; frac is reported against HBM as the "
-                     "north_star asks, tflops/fp32_frac give the binding roof" % FP32_SIMT_PEAK_TFLOPS,
-                fp32_frac=round(main["tflops"] / FP32_SIMT_PEAK_TFLOPS, 4))
+    hbm_view = dict(out[dom])
+    if dom == "conv_rows_tc":
+        # tensor-bound: 3xTF32 executes 3 tf32 MMA flops per fp32-equivalent flop; tf32 dense peak = half the measured
+        # bf16 dense peak (same tcgen05 pipe, K=8 instead of K=16 per instruction)
+        tf32_peak = peak_tf / 2.0
+        executed = 3.0 * hbm_view["tflops"]
+        main = {"bound": "tensor", "achieved": round(executed, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                "frac": round(executed / tf32_peak, 4), "traffic": None, "kernel": dom,
+                "fp32_equivalent_tflops": hbm_view["tflops"], "avg_launch_us": hbm_view["avg_launch_us"],
+                "launches_per_step": hbm_view["launches_per_step"], "share_of_kernel_time": hbm_view["share_of_kernel_time"],
+                "bytes_per_launch": hbm_view["bytes_per_launch"],
+                "hbm_view": {"achieved_gbs": hbm_view["achieved"], "peak_gbs": peak_gbs, "frac": hbm_view["frac"]},
+                "peak_source": peak_src + ": bf16_tflops / 2 for tf32",
+                "note": "tcgen05.mma.kind::tf32, 3 MMAs per fp32 product (hi*hi + hi*lo + lo*hi), fp32 accumulation in "
+                        "TMEM; one issuing thread sustains one MMA per ~200 clk, so with one writer per accumulator "
+                        "(deterministic) the 128x128x8 tiles cap the pipe at ~64 % (DESIGN.md 4)"}
+    else:
+        main = dict(hbm_view)
+        main.update(kernel=dom, peak_source=peak_src,
+                    note="fp32 SIMT kernel; tflops/fp32_frac give the FMA-roof view (%.1f TFLOP/s nominal)" % FP32_SIMT_PEAK_TFLOPS,
+                    fp32_frac=round(main["tflops"] / FP32_SIMT_PEAK_TFLOPS, 4))
     traffic_file = os.path.join(REPO, "profiles", "ncu_traffic.json")
     if os.path.exists(traffic_file):
         try:
@@ -333,7 +354,7 @@ def run_native(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    peak_gbs, peak_src = measured_peaks()
+    peak_gbs, peak_tf, peak_src = measured_peaks()
 
     def setup(wl_name):
         wl = WORKLOADS[wl_name]
@@ -427,7 +448,7 @@ def run_native(args, rank, world, local_rank):
         dec(resident, THRESH)
     torch.cuda.synchronize()
     ops.set_profiler(None)
-    roof, roof_all = roofline_from(prof.results(), peak_gbs, peak_src, prof_steps)
+    roof, roof_all = roofline_from(prof.results(), peak_gbs, peak_tf, peak_src, prof_steps)
 
     # ---- 4. secondary workload of the metric (device-resident only)
     also = None

@@ -378,7 +378,7 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
         ws = None
         if splits > 1:
             ws = _scratch.splitk(dev, lib.wmd_conv_tc_splitk_ws_bytes(max_rows, out.shape[1], splits))
-        with _prof('conv_rows', info):
+        with _prof('conv_rows_tc', info):
             rc = lib.wmd_conv_rows_tc_splitk_f32(ctypes.byref(d), splits, _lib.ptr(ws), ws.numel() * 4 if ws is not None else 0,
                                                  _lib.stream_ptr())
     else:
