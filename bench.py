@@ -379,15 +379,16 @@ def run_native(args, rank, world, local_rank):
         last["out"] = out
 
     # ---- 1. device-resident throughput
+    # clocks are sampled from before the warm-up to the end of the end-to-end pass: the two timed regions are only
+    # tens of milliseconds long, nvidia-smi samples every 100 ms; the "under load" figure is the median of the upper half
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(args.warmup - 1, 0)):
-        step()
     if sampler:
         sampler.start()
+    for _ in range(max(args.warmup - 1, 0)):
+        step()
     l0 = _lib.launch_count()
     ms = time_device(step, args.steps, 1 if args.warmup else 0, dist, world)
     launches = _lib.launch_count() - l0
-    clocks = sampler.stop() if sampler else None
     launches -= (1 if args.warmup else 0) * (launches // (args.steps + (1 if args.warmup else 0)))
     out = last["out"]
     dens = {s: round(float(out[("wavelet_mask", s)].float().mean()), 4) for s in (3, 2, 1, 0)}
@@ -437,6 +438,7 @@ def run_native(args, rank, world, local_rank):
     enqueue_copy(0)
     e2e_ms = time_device(e2e_step, args.steps, 2, dist, world)
     e2e_value = n_global * args.steps / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if sampler else None
     del bufs
 
     # ---- 3. per-kernel roofline pass (same workload, CUDA events around every libwmd launch)
