@@ -158,6 +158,8 @@ def account(name, info):
     if name == "idwt_haar":
         px = info["n"] * info["c"] * info["h"] * info["w"]
         return (32 + (16 if info["disp"] else 0)) * px, 14 * px
+    if name == "idwt_bilinear":
+        return 16 * info["n"] * info["c"] * info["h"] * info["w"] + 4 * info["n"] * info["c"] * info["fh"] * info["fw"], 0
     if name == "dwt_haar":
         return 8 * info["n"] * info["c"] * info["h"] * info["w"], 0
     if name == "range_thresh":

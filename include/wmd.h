@@ -70,6 +70,14 @@ long long wmd_launch_count(void);
 int wmd_idwt_haar_f32(const float* ll, const float* hf, float* out, float* disp, float disp_scale, int clamp01,
                       int N, int C, int H, int W, wmd_stream_t stream);
 
+/* Fused IDWT + disparity epilogue + bilinear resize: full (N,C,full_h,full_w) = bilinear(disp) with
+ * disp = [clamp01](idwt(ll,hf) * disp_scale), PyTorch F.interpolate(mode="bilinear") index arithmetic for either
+ * align_corners setting.  Replaces the consumers of ("disp", s): KITTI/trainer.py:338-339 (align_corners=False),
+ * NYUv2/utils.py:223-227, NYUv2/train.py:305-306 (align_corners=True).  The intermediate disp plane is not read
+ * back from HBM.  Supports upsampling (and downsampling up to ~1.3x). */
+int wmd_idwt_bilinear_f32(const float* ll, const float* hf, float* full, float disp_scale, int clamp01, int full_h,
+                          int full_w, int align_corners, int N, int C, int H, int W, wmd_stream_t stream);
+
 /* Replaces one level of pytorch_wavelets.DWTForward.forward (NYUv2/train.py:258,289); also the
  * adjoint used for the IDWT's backward (KITTI/trainer.py:208-212 trains through inverse_wt).
  *   x (N,C,H,W), H and W even -> ll (N,C,H/2,W/2), hf (N,C,3,H/2,W/2) */

@@ -270,3 +270,18 @@ def test_full_size_haar_round_trip_1024x320_bs32():
     ll2, hf2 = torch.rand_like(ll), torch.rand_like(hf)
     lhs = ops.idwt_haar(ll + ll2, hf + hf2)
     assert rel_err(lhs, rec + ops.idwt_haar(ll2, hf2)) <= 1e-6
+
+
+def test_full_res_consumer_epilogue_matches_trainer_interpolate():
+    """decoder.full_res_size -> ("disp_full", s) == F.interpolate(("disp", s), size, bilinear, align_corners=False)
+    (KITTI/trainer.py:338-339), produced by the fused IDWT+bilinear kernel."""
+    import torch.nn.functional as F
+    _, meta = load_golden("kitti_tiny_dense")
+    mod, _ = _kitti(kd.DepthWaveProgressiveDecoder, meta)
+    mod.full_res_size = (meta["height"], meta["width"])
+    with torch.no_grad():
+        out = mod(kitti_features(meta, DEV))
+    for s in (1, 2, 3):
+        want = F.interpolate(out[("disp", s)], mod.full_res_size, mode="bilinear", align_corners=False)
+        assert float((out[("disp_full", s)] - want).abs().max()) <= 2e-6
+    assert ("disp_full", 0) not in out

@@ -349,3 +349,16 @@ def test_tc_split_k_vs_torch(splits):
                        splits=splits)
     got = ops.scatter_rows(ys, cout, pix, off[n:], n, h, w)
     assert rel_err(got, want * mask.cpu().float()) <= REL_TOL
+
+
+@pytest.mark.parametrize("h,w,size,ac", [(12, 40, (192, 640), False), (24, 80, (192, 640), False), (48, 160, (192, 640), False),
+                                          (30, 40, (240, 320), True), (7, 9, (50, 31), False), (60, 80, (240, 320), True)])
+def test_fused_idwt_bilinear_vs_torch(h, w, size, ac):
+    """disp -> full-resolution bilinear plane straight from the coefficients (trainer.py:338-339, NYUv2/utils.py:223-227)."""
+    n = 2
+    ll, hf = rnd(n, 1, h, w, seed=90, lo=0, hi=8), rnd(n, 1, 3, h, w, seed=91, lo=-2, hi=2)
+    disp = torch.clamp(ohaar.DWTInverse("haar", "zero")((ll, [hf])) / 4, 0, 1)
+    want = F.interpolate(disp, size, mode="bilinear", align_corners=ac)
+    got = ops.idwt_bilinear(ll.to(DEV), hf.to(DEV), size, disp_scale=0.25, clamp01=True, align_corners=ac)
+    assert got.shape == want.shape
+    assert float((got.cpu() - want).abs().max()) <= 2e-6

@@ -56,6 +56,8 @@ SIGNATURES = {
     "wmd_launch_count": (c_longlong, []),
     "wmd_idwt_haar_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int,
                                   c_int, c_void_p]),
+    "wmd_idwt_bilinear_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, c_void_p]),
     "wmd_dwt_haar_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "wmd_range_ws_bytes": (c_size_t, [c_int, c_longlong]),
     "wmd_range_thresh_f32": (c_int, [c_void_p, c_int, c_longlong, c_float, c_void_p, c_void_p, c_void_p, c_size_t,

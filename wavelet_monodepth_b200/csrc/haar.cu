@@ -113,7 +113,87 @@ __global__ void __launch_bounds__(256) dwt_haar_kernel(const float* __restrict__
   }
 }
 
+// Fused IDWT + disparity epilogue + bilinear resize to the full-resolution plane (the consumer of ("disp", s) in
+// KITTI/trainer.py:338-339 and NYUv2/utils.py:223-227).  The upsampled plane is produced straight from the
+// coefficients: a CTA owns a 32 x 128 tile of the FULL-resolution output, synthesises the (tile/f + 2)^2 patch of
+// disp it interpolates from into shared memory (each source pixel = one quadrant of one Haar butterfly, coefficient
+// reads are L1/L2 hits shared by the four quadrants), then every thread blends its outputs.  The disp plane itself
+// is never read back from HBM: 16*H*W coefficient bytes in, 4*Hf*Wf bytes out.
+constexpr int kBT_H = 32, kBT_W = 128;
+constexpr int kBS_MAX = 2048;   // floats of shared source patch (>= (32/f+3) * (128/f+3) for f >= 1.33)
+
+__device__ __forceinline__ float src_index(float scale, int dst, bool align_corners) {
+  if (align_corners) return scale * static_cast<float>(dst);
+  const float s = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  return s < 0.f ? 0.f : s;
+}
+
+__global__ void __launch_bounds__(256) idwt_bilinear_kernel(const float* __restrict__ ll, const float* __restrict__ hf,
+                                                            float* __restrict__ full, float disp_scale, int clamp01,
+                                                            int H, int W, int Hf, int Wf, float sy, float sx,
+                                                            int align_corners) {
+  __shared__ float patch[kBS_MAX];
+  const long long plane = blockIdx.z;
+  const int Y0 = blockIdx.y * kBT_H, X0 = blockIdx.x * kBT_W;
+  const int Hs = 2 * H, Ws = 2 * W;                       // source (disp) plane
+  const int Y1 = min(Y0 + kBT_H, Hf) - 1, X1 = min(X0 + kBT_W, Wf) - 1;
+  // source rows / cols this tile interpolates from
+  const int ys0 = static_cast<int>(src_index(sy, Y0, align_corners));
+  const int ys1 = min(static_cast<int>(src_index(sy, Y1, align_corners)) + 1, Hs - 1);
+  const int xs0 = static_cast<int>(src_index(sx, X0, align_corners));
+  const int xs1 = min(static_cast<int>(src_index(sx, X1, align_corners)) + 1, Ws - 1);
+  const int ph = ys1 - ys0 + 1, pw = xs1 - xs0 + 1;
+  const long long HW = static_cast<long long>(H) * W;
+  const float* pl = ll + plane * HW;
+  const float* phf = hf + plane * 3 * HW;
+  for (int e = threadIdx.x; e < ph * pw; e += blockDim.x) {
+    const int y = ys0 + e / pw, x = xs0 + e % pw;
+    const long long o = static_cast<long long>(y >> 1) * W + (x >> 1);
+    const Quad q = haar_synth(__ldg(pl + o), __ldg(phf + o), __ldg(phf + HW + o), __ldg(phf + 2 * HW + o));
+    const float v = (y & 1) ? ((x & 1) ? q.y11 : q.y10) : ((x & 1) ? q.y01 : q.y00);
+    patch[e] = disp_of(v, disp_scale, clamp01);
+  }
+  __syncthreads();
+  float* out = full + plane * static_cast<long long>(Hf) * Wf;
+  for (int e = threadIdx.x; e < kBT_H * kBT_W; e += blockDim.x) {
+    const int Y = Y0 + e / kBT_W, X = X0 + e % kBT_W;
+    if (Y >= Hf || X >= Wf) continue;
+    const float fy = src_index(sy, Y, align_corners), fx = src_index(sx, X, align_corners);
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+    const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+    const float* r0 = patch + (y0 - ys0) * pw - xs0;
+    const float* r1 = patch + (y1 - ys0) * pw - xs0;
+    out[static_cast<long long>(Y) * Wf + X] =
+        (1.f - ly) * ((1.f - lx) * r0[x0] + lx * r0[x1]) + ly * ((1.f - lx) * r1[x0] + lx * r1[x1]);
+  }
+}
+
 }  // namespace wmd
+
+extern "C" int wmd_idwt_bilinear_f32(const float* ll, const float* hf, float* full, float disp_scale, int clamp01,
+                                     int full_h, int full_w, int align_corners, int N, int C, int H, int W,
+                                     wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(ll && hf && full, WMD_ERR_ARG);
+  WMD_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0 && full_h > 0 && full_w > 0, WMD_ERR_SHAPE);
+  const long long planes = static_cast<long long>(N) * C;
+  if (planes == 0) return WMD_OK;
+  WMD_REQUIRE(planes <= 65535, WMD_ERR_SHAPE);
+  const int Hs = 2 * H, Ws = 2 * W;
+  // PyTorch's area_pixel_compute_scale: in/out, or (in-1)/(out-1) with align_corners
+  const float sy = align_corners ? (full_h > 1 ? static_cast<float>(Hs - 1) / static_cast<float>(full_h - 1) : 0.f)
+                                 : static_cast<float>(Hs) / static_cast<float>(full_h);
+  const float sx = align_corners ? (full_w > 1 ? static_cast<float>(Ws - 1) / static_cast<float>(full_w - 1) : 0.f)
+                                 : static_cast<float>(Ws) / static_cast<float>(full_w);
+  // shared patch must hold the tile's source footprint (upsampling or mild downsampling only)
+  const long long need = (static_cast<long long>(kBT_H * sy) + 4) * (static_cast<long long>(kBT_W * sx) + 4);
+  WMD_REQUIRE(need <= kBS_MAX, WMD_ERR_UNSUPPORTED);
+  dim3 grid(ceil_div(full_w, kBT_W), ceil_div(full_h, kBT_H), static_cast<unsigned>(planes));
+  idwt_bilinear_kernel<<<grid, 256, 0, as_stream(stream)>>>(ll, hf, full, disp_scale, clamp01, H, W, full_h, full_w, sy, sx,
+                                                          align_corners);
+  return launched();
+}
 
 extern "C" int wmd_idwt_haar_f32(const float* ll, const float* hf, float* out, float* disp, float disp_scale,
                                  int clamp01, int N, int C, int H, int W, wmd_stream_t stream) {

@@ -125,6 +125,11 @@ class _WaveDecoderBase(nn.Module):
         self.decoder = nn.ModuleList(list(self.convs.values()))
         self.sigmoid = nn.Sigmoid()
         self._packs = _PackCache()
+        # optional fused consumer epilogue (not part of the reference's decoder, off by default): when set to (H, W),
+        # inference also returns ("disp_full", s) = F.interpolate(("disp", s), (H, W), mode="bilinear",
+        # align_corners=False) for s = 1..3 - what KITTI/trainer.py:338-339 computes from every scale - produced
+        # straight from the coefficients by the fused IDWT+bilinear kernel
+        self.full_res_size = None
 
     # ---- packed parameters ------------------------------------------------------------------
     def _upconv(self, i, j):
@@ -243,6 +248,9 @@ class _WaveDecoderBase(nn.Module):
             out[("wavelets", i - 1, "LH")] = yh[:, 0:1]
             out[("wavelets", i - 1, "HL")] = yh[:, 1:2]
             out[("wavelets", i - 1, "HH")] = yh[:, 2:3]
+            if self.full_res_size is not None and i > 1:
+                out[("disp_full", i - 1)] = ops.idwt_bilinear(yl, yh.unsqueeze(1), self.full_res_size,
+                                                               disp_scale=1.0 / 2 ** (i - 1), clamp01=True)
             yl, disp = ops.idwt_haar(yl, yh.unsqueeze(1), disp_scale=1.0 / 2 ** (i - 1), clamp01=True)
             out[("disp", i - 1)] = disp
             x_rows, x_c = xb, c

@@ -120,6 +120,21 @@ def idwt_haar(ll, hf, disp_scale=None, clamp01=False):
     return (out, disp) if disp_scale is not None else out
 
 
+def idwt_bilinear(ll, hf, size, disp_scale=1.0, clamp01=False, align_corners=False):
+    """Fused IDWT -> disp = [clamp](out*disp_scale) -> bilinear resize to `size` (F.interpolate semantics)."""
+    lib = _lib.load()
+    ll, hf = _dense(ll), _dense(hf)
+    n, c, h, w = ll.shape
+    full = torch.empty((n, c, int(size[0]), int(size[1])), dtype=_f32, device=ll.device)
+    if full.numel() == 0:
+        return full
+    with _prof('idwt_bilinear', lambda: dict(n=n, c=c, h=h, w=w, fh=int(size[0]), fw=int(size[1]))):
+        rc = lib.wmd_idwt_bilinear_f32(_lib.ptr(ll), _lib.ptr(hf), _lib.ptr(full), float(disp_scale), int(bool(clamp01)),
+                                       int(size[0]), int(size[1]), int(bool(align_corners)), n, c, h, w, _lib.stream_ptr())
+    _lib.check(rc, "wmd_idwt_bilinear_f32")
+    return full
+
+
 def dwt_haar(x):
     """x (N,C,H,W) even H,W -> ll (N,C,H/2,W/2), hf (N,C,3,H/2,W/2)."""
     lib = _lib.load()
