@@ -46,10 +46,12 @@ for name, h, w, c0, c1, cout, taps, dens in LAYERS:
     res = {}
     outs = {}
     for kind in kinds:
-        wp = ops.pack_weight(wt, c1, kind=kind)
+        wp = ops.pack_weight(wt, c1, kind=kind.split("@")[0])      # "tc@0" / "tc@1" / "tc@3": force the split mode
         kw = dict(taps=taps, pad=PAD_REFLECT, act=ACT_ELU, shift0=1 if c1 else 0, x1=x1, c1=c1)
         if pixels is not None:
             kw.update(pixels=pixels, count=count)
+        if "@" in kind:
+            kw.update(splits=int(kind.split("@")[1]))
         for _ in range(2):
             y = ops.conv_rows(x0, c0, wp, bias, cout, n, h, w, **kw)
         torch.cuda.synchronize()

@@ -330,7 +330,7 @@ def test_factored_head_vs_torch(c, kind):
     assert rel_err(got_s, want * mask.cpu().float()) <= REL_TOL
 
 
-@pytest.mark.parametrize("splits", [2, 3, 4])
+@pytest.mark.parametrize("splits", [0, 2, 3, 4])
 def test_tc_split_k_vs_torch(splits):
     """Split-K work items + fixed-order reduce pass give the same convolution (and are deterministic)."""
     n, cin, cout, h, w = 2, 160, 128, 9, 13

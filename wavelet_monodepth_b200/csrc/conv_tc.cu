@@ -236,15 +236,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   __syncthreads();
   tc_fence_after();
 
-  // work item = (output tile, K split): with split-K the chunk range [cb, ce) of the reduction is handled here and
-  // the raw partial sums go to a workspace (summed, biased and activated by splitk_reduce_kernel) - more, shorter
-  // items fill the 148 SMs evenly when a layer has few tiles
-  const long long items = tiles * splits;
-  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const long long tile = item / splits;
-    const int ks = static_cast<int>(item - tile * splits);
-    const int cb = static_cast<int>(static_cast<long long>(ks) * nchunks / splits);
-    const int ce = static_cast<int>(static_cast<long long>(ks + 1) * nchunks / splits);
+  // Work decomposition.  A "unit" is one 32-channel chunk of one output tile.
+  //   splits >= 1 : every tile's reduction is cut into `splits` equal ranges (split-K); splits == 1 = whole tiles.
+  //   splits == 0 : BALANCED - the tiles x nchunks units are dealt out to the CTAs in equal contiguous ranges of U
+  //                 units (stream-K style), so the SMs finish together however many tiles the (device-side) row
+  //                 count yields.  A tile cut by a range boundary has <= 4 segments (U >= nchunks/3).
+  // Segments that do not cover a whole tile write raw partial sums to workspace slab `slab`; tc_reduce_kernel sums
+  // the slabs in a fixed order and applies bias + activation, so results stay deterministic.
+  const bool balanced = (splits == 0);
+  const long long total_units = tiles * nchunks;
+  const long long U = balanced ? max((total_units + gridDim.x - 1) / gridDim.x, static_cast<long long>((nchunks + 2) / 3)) : 0;
+  long long u = balanced ? static_cast<long long>(blockIdx.x) * U : 0;
+  const long long u_end = balanced ? min(total_units, u + U) : 0;
+  long long item = blockIdx.x;
+  const long long items = balanced ? 0 : tiles * splits;
+  while (true) {
+    long long tile;
+    int cb, ce, slab;
+    bool whole;
+    if (balanced) {
+      if (u >= u_end) break;
+      tile = u / nchunks;
+      cb = static_cast<int>(u - tile * nchunks);
+      ce = static_cast<int>(min(static_cast<long long>(nchunks), cb + (u_end - u)));
+      slab = static_cast<int>(blockIdx.x - (tile * nchunks) / U);
+      whole = (cb == 0 && ce == nchunks);
+      u += ce - cb;
+    } else {
+      if (item >= items) break;
+      tile = item / splits;
+      slab = static_cast<int>(item - tile * splits);
+      cb = static_cast<int>(static_cast<long long>(slab) * nchunks / splits);
+      ce = static_cast<int>(static_cast<long long>(slab + 1) * nchunks / splits);
+      whole = (splits == 1);
+      item += gridDim.x;
+    }
     const int len = ce - cb;
     const int m0 = static_cast<int>(tile / n_tiles) * TC_BM;
     const int nt = static_cast<int>(tile % n_tiles);
@@ -470,13 +496,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       tc_fence_after();
       drain();
       const int m = m0 + my_row;
-      if (m < rows && splits > 1) {
-        // raw partial sums of this K split (bias / activation are applied by the reduce pass)
-        float* pr = partial + (static_cast<long long>(ks) * d.max_rows + m) * d.ldy;
+      if (m < rows && !whole) {
+        // raw partial sums of this segment (bias / activation are applied by the reduce pass)
+        float* pr = partial + (static_cast<long long>(slab) * d.max_rows + m) * d.ldy;
 #pragma unroll
-        for (int j = 0; j < ACC; ++j) {
-          const int co = n0 + my_ch * ACC + j;
-          if (co < d.cout) pr[co] = acc[j];
+        for (int j = 0; j < ACC; j += 4) {
+          const int co = n0 + my_ch * ACC + j;       // ldy % 4 == 0: a quad that starts below cout stays inside the row
+          if (co < d.cout) *reinterpret_cast<float4*>(pr + co) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
       } else if (m < rows) {
         float* yr = d.y + static_cast<long long>(m) * d.ldy;
@@ -552,21 +578,56 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
   }
 }
 
-// y[m, co] = act(bias[co] + sum_s partial[s][m][co]) in a fixed order (deterministic)
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ bias,
-                                     float* __restrict__ y, int ldy, int cout, const int32_t* __restrict__ count,
-                                     int max_rows, int act, float act_param) {
+// y[m, co] = act(bias[co] + sum_s partial[s][m][co]) in a fixed order (deterministic).  splits >= 2: every tile has
+// `splits` slabs.  splits == 0 (balanced): the number of slabs of a tile follows from the same unit arithmetic the
+// conv kernel used (grid = its CTA count); tiles that one CTA covered entirely were already finished there.
+__global__ void tc_reduce_kernel(const float* __restrict__ partial, int splits, int grid, int BN, int nchunks,
+                                 const float* __restrict__ bias, float* __restrict__ y, int ldy, int cout,
+                                 const int32_t* __restrict__ count, int max_rows, int act, float act_param) {
   const int rows = count ? min(*count, max_rows) : max_rows;
-  const long long total = static_cast<long long>(rows) * cout;
-  const long long slab = static_cast<long long>(max_rows) * ldy;
-  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += step) {
-    const long long m = i / cout;
-    const int co = static_cast<int>(i - m * cout);
-    const long long o = m * ldy + co;
-    float v = bias ? __ldg(bias + co) : 0.f;
-    for (int sidx = 0; sidx < splits; ++sidx) v += __ldg(partial + sidx * slab + o);
-    y[o] = activate(v, act, act_param);
+  const long long slab_sz = static_cast<long long>(max_rows) * ldy;
+  const int n_tiles = (cout + BN - 1) / BN;
+  const long long tiles = static_cast<long long>((rows + TC_BM - 1) / TC_BM) * n_tiles;
+  const long long total_units = tiles * nchunks;
+  const long long U = splits == 0 ? max((total_units + grid - 1) / grid, static_cast<long long>((nchunks + 2) / 3)) : 0;
+  const int quads = BN >> 2;                         // float4 columns of a tile (ldy is a multiple of 4)
+  // one CTA per tile per round: the slab arithmetic is per tile, the element loop has no divisions by run-time values
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    int nslabs = splits;
+    if (splits == 0) {
+      const long long first = (tile * nchunks) / U, last = ((tile + 1) * nchunks - 1) / U;
+      if (first == last) continue;                   // whole tile: already written with bias + activation
+      nslabs = static_cast<int>(last - first + 1);
+    }
+    const int m0 = static_cast<int>(tile / n_tiles) * TC_BM;
+    const int co0 = static_cast<int>(tile % n_tiles) * BN;
+    const int mrows = min(TC_BM, rows - m0);
+    for (int e = threadIdx.x; e < mrows * quads; e += blockDim.x) {
+      const int r = e / quads, q = e - r * quads;    // quads is a power of two times {8,16,32}: cheap 32-bit division
+      const int co = co0 + (q << 2);
+      if (co >= cout) continue;
+      const long long o = static_cast<long long>(m0 + r) * ldy + co;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) {
+        v.x = __ldg(bias + co);
+        if (co + 1 < cout) v.y = __ldg(bias + co + 1);
+        if (co + 2 < cout) v.z = __ldg(bias + co + 2);
+        if (co + 3 < cout) v.w = __ldg(bias + co + 3);
+      }
+      for (int sidx = 0; sidx < nslabs; ++sidx) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(partial + sidx * slab_sz + o));
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+      }
+      v.x = activate(v.x, act, act_param); v.y = activate(v.y, act, act_param);
+      v.z = activate(v.z, act, act_param); v.w = activate(v.w, act, act_param);
+      if (co + 3 < cout) {
+        *reinterpret_cast<float4*>(y + o) = v;
+      } else {
+        y[o] = v.x;
+        if (co + 1 < cout) y[o + 1] = v.y;
+        if (co + 2 < cout) y[o + 2] = v.z;
+      }
+    }
   }
 }
 
@@ -584,15 +645,16 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
     if (rc != WMD_OK) return rc;
     attr_done[dev] = true;
   }
-  const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN) * splits;
+  const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN) * (splits > 0 ? splits : 1);
   const long long cap = sm_count();
-  const int grid = static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
+  const int grid = splits == 0 ? static_cast<int>(cap) : static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
   conv_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial);
   int rc = launched();
   if (rc != WMD_OK || splits == 1) return rc;
-  const long long total = static_cast<long long>(d.max_rows) * d.cout;
-  splitk_reduce_kernel<<<stride_grid(total, 256), 256, 0, stream>>>(partial, splits, d.bias, d.y, d.ldy, d.cout, d.count,
-                                                                  d.max_rows, d.act, d.act_param);
+  const int nchunks = d.taps * ((d.c0 + TC_BK - 1) / TC_BK + (d.c1 + TC_BK - 1) / TC_BK);
+  const long long all_tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN);
+  tc_reduce_kernel<<<static_cast<int>(all_tiles < 8 * cap ? all_tiles : 8 * cap), 256, 0, stream>>>(partial, splits, grid, BN, nchunks, d.bias, d.y, d.ldy, d.cout,
+                                                              d.count, d.max_rows, d.act, d.act_param);
   return launched();
 }
 
@@ -619,7 +681,9 @@ extern "C" int wmd_pack_conv_weight_tc_f32(const float* w, float* packed, int Co
 }
 
 extern "C" size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits) {
-  return splits <= 1 ? 0 : static_cast<size_t>(splits) * static_cast<size_t>(max_rows) * static_cast<size_t>(ldy) * sizeof(float);
+  if (splits == 1) return 0;
+  const size_t slabs = splits == 0 ? 4 : static_cast<size_t>(splits);      // balanced mode: <= 4 segments per tile
+  return slabs * static_cast<size_t>(max_rows) * static_cast<size_t>(ldy) * sizeof(float);
 }
 
 extern "C" int wmd_conv_rows_tc_f32(const wmd_conv_desc* dp, wmd_stream_t stream) {
@@ -630,7 +694,7 @@ extern "C" int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* dp, int splits, 
                                            wmd_stream_t stream) {
   using namespace wmd;
   WMD_REQUIRE(dp, WMD_ERR_ARG);
-  WMD_REQUIRE(splits >= 1 && splits <= 16, WMD_ERR_ARG);
+  WMD_REQUIRE(splits >= 0 && splits <= 16, WMD_ERR_ARG);
   WMD_REQUIRE(splits == 1 || (ws != nullptr && ws_bytes >= wmd_conv_tc_splitk_ws_bytes(dp->max_rows, dp->ldy, splits)),
               WMD_ERR_WORKSPACE);
   wmd_conv_desc d = *dp;
@@ -649,6 +713,9 @@ extern "C" int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* dp, int splits, 
               WMD_ERR_SHAPE);
   WMD_REQUIRE((reinterpret_cast<uintptr_t>(d.w) & 15) == 0, WMD_ERR_SHAPE);
   WMD_REQUIRE(d.ldy >= d.cout, WMD_ERR_SHAPE);
+  // the partial-sum passes move float4s
+  WMD_REQUIRE(splits == 1 || (d.ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(d.y) & 15) == 0 &&
+                              (reinterpret_cast<uintptr_t>(ws) & 15) == 0), WMD_ERR_SHAPE);
   if (d.shift0 == 1) WMD_REQUIRE(d.H % 2 == 0 && d.W % 2 == 0, WMD_ERR_SHAPE);
   if (d.pad_mode == WMD_PAD_REFLECT && d.taps == 9) WMD_REQUIRE(d.H >= 2 && d.W >= 2, WMD_ERR_SHAPE);
   // tap tables hold 32-bit offsets in 16-byte units
@@ -659,6 +726,7 @@ extern "C" int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* dp, int splits, 
   {
     const int nchunks = d.taps * ((d.c0 + TC_BK - 1) / TC_BK + (d.c1 + TC_BK - 1) / TC_BK);
     if (splits > nchunks) splits = nchunks;      // every split needs at least one chunk
+    if (splits == 0 && nchunks < 2) splits = 1;   // nothing to balance inside a one-chunk reduction
   }
   float* partial = static_cast<float*>(ws);
   switch (tc_tile_n(d.cout)) {

@@ -283,28 +283,31 @@ def scatter_rows(rows, c, pixels, count, n, h, w, max_rows=None, out=None):
 _sm_count = {}
 
 
-def tc_splits(max_rows, cout, nchunks, device):
-    """Split-K factor for the tcgen05 engine.
+TC_BALANCE_WS_LIMIT = 2 << 30      # bytes of partial-sum workspace we are willing to hold for balanced scheduling
 
-    tiles = ceil(rows/256) * ceil(cout/N) equal work items run on one CTA per SM.  Splitting the reduction only pays
-    when the layer cannot even fill the SMs once (measured: the partial-sum pass and the per-item prologue eat the
-    gain otherwise), e.g. the coarsest level (R50 1024x320 bs32 upconv(4,0): 80 tiles -> 3 splits, 0.78 -> 0.63 ms)
-    and small batches.  Every split keeps >= 8 chunks."""
+
+def tc_splits(max_rows, cout, nchunks, device, ldy=None):
+    """Scheduling mode of the tcgen05 engine for one launch: 1 = whole tiles, 0 = balanced (stream-K style).
+
+    One CTA per SM runs equal (256-row x N-channel) tiles, so with few tiles per SM the last round is mostly idle
+    (320 tiles on 148 SMs = 72 %) and a layer with fewer tiles than SMs leaves SMs dark.  Balanced mode deals the
+    (tile, chunk) units out evenly on the device and finishes cut tiles with a fixed-order reduce pass; it costs one
+    extra write + read of the cut tiles' outputs, which only pays for long reductions.  Measured on B200 (R50 1024x320,
+    scripts/conv_layers_bench.py): bs32 upconv(4,0) 0.85 -> 0.55 ms, upconv(4,1) 1.62 -> 1.36, upconv(3,1) 0.87 -> 0.71,
+    upconv(2,1) 0.75 -> 0.69; the 1x1 head stages (1-8 chunks) and the short 3x3 reductions (<= 72 chunks) lose 5-25 %
+    at bs32 but win when the launch cannot fill the SMs (bs4 upconv(3,0) 0.133 -> 0.098).
+    Needs a workspace of 4 x max_rows x ldy floats."""
     lib = _lib.load()
+    ldy = pad4(cout) if ldy is None else ldy
+    if 16 * max_rows * ldy > TC_BALANCE_WS_LIMIT:
+        return 1
+    if nchunks >= 80:
+        return 0
     key = str(device)
     if key not in _sm_count:
         _sm_count[key] = torch.cuda.get_device_properties(device).multi_processor_count
-    sms = _sm_count[key]
-    bn = lib.wmd_conv_tc_tile_n(cout)
-    tiles = -(-max_rows // 256) * -(-cout // bn)
-    if tiles > 0.75 * sms:
-        return 1
-    best = 1
-    for s in (2, 3, 4):
-        if nchunks // s < 8 or tiles * s > 1.7 * sms:
-            break
-        best = s
-    return best
+    tiles = -(-max_rows // 256) * -(-cout // lib.wmd_conv_tc_tile_n(cout))
+    return 0 if (nchunks >= 32 and tiles <= 0.75 * _sm_count[key]) else 1
 
 
 class PackedW:
@@ -389,9 +392,9 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
     info = lambda: dict(n=n, h=h, w=w, taps=taps, c0=c0, c1=c1, cout=cout, shift0=shift0, count=count,   # noqa: E731
                         max_rows=max_rows, m_in0=m_in0, m_in1=m_in1, kind=wpacked.kind)
     if wpacked.kind == "tc":
-        splits = tc_splits(max_rows, cout, taps * (-(-c0 // 32) + -(-c1 // 32)), dev) if splits is None else splits
+        splits = tc_splits(max_rows, cout, taps * (-(-c0 // 32) + -(-c1 // 32)), dev, out.shape[1]) if splits is None else splits
         ws = None
-        if splits > 1:
+        if splits != 1:
             ws = _scratch.splitk(dev, lib.wmd_conv_tc_splitk_ws_bytes(max_rows, out.shape[1], splits))
         with _prof('conv_rows_tc', info):
             rc = lib.wmd_conv_rows_tc_splitk_f32(ctypes.byref(d), splits, _lib.ptr(ws), ws.numel() * 4 if ws is not None else 0,
