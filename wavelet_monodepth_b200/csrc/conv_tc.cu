@@ -72,6 +72,16 @@ __device__ unsigned int g_dbg[4];
 #define MBAR_FAIL(id) __trap()
 #define MBAR_SPINS (1u << 28)
 #endif
+// -DWMD_TC_TRACE (scripts/tc_trace.py builds a separate library): CTA 0 records clock64() at fixed points of the
+// first kTraceChunks chunks for producer warp 0, producer warp 11 and issuer 0.
+#ifdef WMD_TC_TRACE
+constexpr int kTraceChunks = 256, kTraceSlots = 8;
+__device__ long long g_trace[3 * kTraceSlots * kTraceChunks];
+#define TC_TRACE(role, slot, c) do { if (blockIdx.x == 0 && lane == 0 && (c) < kTraceChunks) \
+    g_trace[((role) * kTraceSlots + (slot)) * kTraceChunks + (c)] = clock64(); } while (0)
+#else
+#define TC_TRACE(role, slot, c) do {} while (0)
+#endif
 // bounded spin: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t id = 0) {
   uint32_t done = 0;
@@ -116,6 +126,12 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(p));
+  return p != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
@@ -174,7 +190,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   __shared__ __align__(8) uint64_t bar_epoch;              // accumulation epoch complete (4 issuers)
   __shared__ uint32_t tmem_base_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches and everything the issuer warps
+  // compute from it stay on the uniform datapath (see the issuer section)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const bool is_producer = warp < TC_PROD_WARPS;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* sA_base = base;
@@ -381,13 +399,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
         const uint32_t tstage = round & 1;
+        const int trole = warp == 0 ? 0 : (warp == TC_PROD_WARPS - 1 ? 1 : 3);
+        if (trole < 3) TC_TRACE(trole, 0, c);
         cp_async_wait<0>();
+        if (trole < 3) TC_TRACE(trole, 1, c);
         producer_barrier();                          // raw A tile of chunk c complete; split reads of chunk c-1 done
+        if (trole < 3) TC_TRACE(trole, 2, c);
         if (c + 1 < len) {
           load_a(cb + c + 1, (c + 1) & 1);
           if (c + 1 + kPrefetchAhead < len) prefetch_chunk(cb + c + 1 + kPrefetchAhead);
         }
         cp_async_commit();
+        if (trole < 3) TC_TRACE(trole, 3, c);
         if ((c % kFlushChunks) == 0 && c > 0) {      // epoch boundary: everybody drains before the next epoch starts
           mbar_wait(smem_u32(&bar_epoch), (epochs - 1) & 1, 0x10000u + round);
           tc_fence_after();
@@ -399,6 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         // TMEM A stage free?  It was read by the MMAs of round-2.
         if (round >= 2) mbar_wait(smem_u32(&bar_mma[tstage]), ((round - 2) >> 1) & 1, 0x20000u + round);
         tc_fence_after();
+        if (trole < 3) TC_TRACE(trole, 4, c);
         // split my (row, 8 channels) slots: u = half*4 + channel-quarter, u = wt, wt+3, wt+6
         {
           const unsigned char* tile_a = sA_base + (c & 1) * TC_A_TILE;
@@ -423,24 +447,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
               tmem_st8(ta + 32u, lo);
             }
           }
+          if (trole < 3) TC_TRACE(trole, 5, c);
           asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_asplit[tstage]));
+        if (trole < 3) TC_TRACE(trole, 6, c);
         if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
       }
     } else {
       // =================================================================================== issuers
-      const int kstep = warp - TC_PROD_WARPS;        // this issuer's k-step inside every chunk
-      if (kstep == 0 && lane == 0) {
+      // The whole warp runs the loop and one elected lane issues.  Written this way (warp-uniform control flow,
+      // operands derived from warp-uniform values) ptxas keeps the MMA operands in uniform registers and emits the
+      // UTCHMMAs back to back: ~78 clk per instruction.  A `lane == 0` branch instead makes it wrap every MMA in an
+      // ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~210 clk (scripts/bench_cu/mma_rate*.cu).
+      const int kstep = warp - TC_PROD_WARPS;        // this issuer's index
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_acc, 0);
+      const uint32_t sB_u = __shfl_sync(0xffffffffu, smem_u32(sB_base), 0);
+      if (kstep == 0 && elect_one()) {
         const unsigned char* w0 = wtile + static_cast<long long>(cb) * (2 * TC_B_TILE);
-        bulk_g2s(smem_u32(sB_base + (round0 % TC_B_STAGES) * 2 * TC_B_TILE), w0, 2 * TC_B_TILE,
-                 smem_u32(&bar_b[round0 % TC_B_STAGES]));
+        bulk_g2s(sB_u + (round0 % TC_B_STAGES) * 2 * TC_B_TILE, w0, 2 * TC_B_TILE, smem_u32(&bar_b[round0 % TC_B_STAGES]));
         if (len > 1)
-          bulk_g2s(smem_u32(sB_base + ((round0 + 1) % TC_B_STAGES) * 2 * TC_B_TILE), w0 + 2 * TC_B_TILE, 2 * TC_B_TILE,
+          bulk_g2s(sB_u + ((round0 + 1) % TC_B_STAGES) * 2 * TC_B_TILE, w0 + 2 * TC_B_TILE, 2 * TC_B_TILE,
                    smem_u32(&bar_b[(round0 + 1) % TC_B_STAGES]));
       }
+      __syncwarp();
+      // issuer -> (M half, accumulator copy); it alone writes that accumulator
+      const int ih = kstep / COPIES, icp = kstep % COPIES;
+      const uint32_t dh = tmem_u + static_cast<uint32_t>((ih * COPIES + icp) * BN);
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
         const uint32_t tstage = round & 1;
@@ -453,38 +488,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           __syncthreads();
           tc_fence_after();
         }
-        if (lane == 0 && kstep < TC_ISSUERS) {
+        if (kstep < TC_ISSUERS) {
+          if (kstep == 0) TC_TRACE(2, 0, c);
           mbar_wait(smem_u32(&bar_asplit[tstage]), (round >> 1) & 1, 0x30000u + round);           // split A of this chunk is in TMEM
+          if (kstep == 0) TC_TRACE(2, 1, c);
           mbar_wait(smem_u32(&bar_b[bs]), (round / TC_B_STAGES) & 1, 0x40000u + round);           // weight image has landed
+          if (kstep == 0) TC_TRACE(2, 2, c);
           tc_fence_after();
-          const uint64_t b0 = umma_desc_sw128(smem_u32(sB_base + bs * 2 * TC_B_TILE));
-          // issuer -> (M half, accumulator copy); it alone writes that accumulator
-          const int ih = kstep / COPIES, icp = kstep % COPIES;
-          const uint32_t dh = tmem_acc + static_cast<uint32_t>((ih * COPIES + icp) * BN);
-          const uint32_t ah = tmem_acc + 256u + tstage * 128u + static_cast<uint32_t>(ih * 64);
+          const uint64_t b0 = umma_desc_sw128(sB_u + bs * 2 * TC_B_TILE);
+          const uint32_t ah = tmem_u + 256u + tstage * 128u + static_cast<uint32_t>(ih * 64);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            if ((ks % COPIES) == icp) {
-              const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
-              const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
-              const uint32_t a = ah + static_cast<uint32_t>(8 * ks);
-              umma_tf32_ts(dh, a + 32u, bh, kIdesc, 1u);     // lo*hi
-              umma_tf32_ts(dh, a, bl, kIdesc, 1u);           // hi*lo
-              umma_tf32_ts(dh, a, bh, kIdesc, 1u);           // hi*hi
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+              if ((ks % COPIES) == icp) {
+                const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
+                const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
+                const uint32_t a = ah + static_cast<uint32_t>(8 * ks);
+                umma_tf32_ts(dh, a + 32u, bh, kIdesc, 1u);     // lo*hi
+                umma_tf32_ts(dh, a, bl, kIdesc, 1u);           // hi*lo
+                umma_tf32_ts(dh, a, bh, kIdesc, 1u);           // hi*hi
+              }
             }
-          }
-          umma_commit(smem_u32(&bar_mma[tstage]));
-          if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) umma_commit(smem_u32(&bar_epoch));
-          // weights two chunks ahead: that B stage was last read by round-2, and all of round-2's MMAs are known to
-          // be complete - the producers only stored this chunk's A (bar_asplit, awaited above) after bar_mma(round-2).
-          // (Waiting on bar_mma here would alias: this round's own commits may already have flipped its phase.)
-          if (kstep == 0 && c + 2 < len) {
-            const uint32_t ns = (round + 2) % TC_B_STAGES;
-            bulk_g2s(smem_u32(sB_base + ns * 2 * TC_B_TILE), wtile + static_cast<long long>(cb + c + 2) * (2 * TC_B_TILE),
-                     2 * TC_B_TILE, smem_u32(&bar_b[ns]));
+            umma_commit(smem_u32(&bar_mma[tstage]));
+            if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) umma_commit(smem_u32(&bar_epoch));
+            // weights two chunks ahead: that B stage was last read by round-2, and all of round-2's MMAs are known to
+            // be complete - the producers only stored this chunk's A (bar_asplit, awaited above) after bar_mma(round-2).
+            // (Waiting on bar_mma here would alias: this round's own commits may already have flipped its phase.)
+            if (kstep == 0 && c + 2 < len) {
+              const uint32_t ns = (round + 2) % TC_B_STAGES;
+              bulk_g2s(sB_u + ns * 2 * TC_B_TILE, wtile + static_cast<long long>(cb + c + 2) * (2 * TC_B_TILE),
+                       2 * TC_B_TILE, smem_u32(&bar_b[ns]));
+            }
           }
         }
         __syncwarp();
+        if (kstep == 0) TC_TRACE(2, 3, c);
         if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
       }
     }
@@ -659,6 +697,12 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
 }
 
 }  // namespace wmd
+
+#ifdef WMD_TC_TRACE
+extern "C" int wmd_debug_tc_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, wmd::g_trace, sizeof(wmd::g_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int wmd_conv_tc_tile_n(int cout) { return wmd::tc_tile_n(cout); }
 
