@@ -1,5 +1,5 @@
 """Phase timing of the tcgen05 conv kernel: builds libwmd_trace.so (-DWMD_TC_TRACE), runs one layer and prints the
-mean clocks between the trace points of CTA 0 (producer warp 0, producer warp 11, issuer 0).
+mean clocks between the trace points of CTA 0 (split warp 0, gather warp 8, issuer 0).
 
     python scripts/tc_trace.py build          # here (cross-compile)
     python scripts/tc_trace.py run [layer]    # on the GPU box
@@ -13,11 +13,11 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from wavelet_monodepth_b200 import build as wbuild   # noqa: E402
 
-TRACE_LIB = os.path.join(REPO, "scripts", "bench_cu", "_bin", "libwmd_trace.so")
+TRACE_LIB = os.path.join(REPO, "scripts", "bench_cu", "_bin", "libwmd_trace%s.so" % os.environ.get("WMD_TRACE_TAG", ""))
 
 if sys.argv[1] == "build":
     os.makedirs(os.path.dirname(TRACE_LIB), exist_ok=True)
-    cmd = [wbuild.nvcc_path(), "-DWMD_TC_TRACE"] + wbuild.NVCC_FLAGS + ["-I", os.path.join(REPO, "include"), "-I", wbuild.CSRC,
+    cmd = [wbuild.nvcc_path(), "-DWMD_TC_TRACE"] + os.environ.get("WMD_TRACE_FLAGS", "").split() + wbuild.NVCC_FLAGS + ["-I", os.path.join(REPO, "include"), "-I", wbuild.CSRC,
                                                                        "-o", TRACE_LIB] + wbuild.sources()
     subprocess.run(cmd, check=True)
     print(TRACE_LIB)
@@ -55,9 +55,9 @@ nch = taps * (-(-c0 // 32) + -(-c1 // 32))
 lo, hi = 40, min(K, nch) - 8                       # steady state of the first tile (skips the epoch boundaries' neighbours)
 sel = [c for c in range(lo, hi) if c % 32 not in (0, 1, 31)]
 print("%s: %d chunks/tile; clocks per chunk (mean over %d steady chunks)" % (name, nch, len(sel)))
-for role, nm, labels in ((0, "producer warp 0", ["cp.async wait", "producer barrier", "issue next gather", "wait MMA(c-2)", "LDS+split+tcgen05.st", "wait::st + arrive", "loop"]),
-                         (1, "producer warp 11", ["cp.async wait", "producer barrier", "issue next gather", "wait MMA(c-2)", "LDS+split+tcgen05.st", "wait::st + arrive", "loop"]),
-                         (2, "issuer 0", ["wait split A", "wait B", "issue 12 MMA + commit", "loop"])):
+for role, nm, labels in ((0, "split warp 0", ["wait raw A", "wait MMA(c-2)", "LDS+split+tcgen05.st", "wait::st + arrive", "loop"]),
+                         (1, "gather warp 8", ["wait raw stage free", "issue gather c+2", "wait gather c + arrive", "loop"]),
+                         (2, "issuer 0", ["wait split A", "wait B", "issue 12 MMA + commit (+B load)", "loop"])):
     tt = t[role]
     npts = len(labels)
     period = np.mean([tt[0, c + 1] - tt[0, c] for c in sel])

@@ -1,62 +1,66 @@
 // K5-TC: the gather-GEMM convolution on 5th-gen tensor cores (tcgen05 + TMEM), fp32-faithful via 3xTF32.
 //
-// Same contract as conv_rows_kernel (conv.cu), different engine.  One CTA per SM owns a 256 x 128 output tile
-// (two UMMA M=128 halves sharing one B tile) and walks K = taps x (c0 + c1) in 32-channel chunks.
+// Same contract as conv_rows_kernel (conv.cu), different engine.  One CTA per SM owns a 256 x N output tile
+// (two UMMA M=128 halves sharing one B tile, N = 128 / 64 / 32) and walks K = (c0 + c1) x taps in 32-channel chunks,
+// the taps of a channel chunk innermost (their source rows overlap: L2 hits).
 // Warp-specialised, mbarrier-pipelined (no CTA-wide barrier inside the K loop):
 //
-//   producers (warps 0-11)
-//     * gather A (implicit im2col: 256 rows x 32 channels) with 16-byte zero-filling cp.async into a raw fp32,
-//       128B-swizzled shared tile (lanes = adjacent pieces of a row: 4 lines per warp request; rows come from an
-//       index-map gather, which a TMA tile load cannot express), L2-prefetched a few chunks ahead;
-//     * then each thread owns (row, 8 channels) slots: reads them back (the swizzle makes this transposed read
-//       conflict-free), splits x = hi + lo (hi = x with the 13 low mantissa bits cleared, lo = x - hi: exact) and
-//       writes hi / lo into TENSOR MEMORY with tcgen05.st - the MMAs take A from TMEM (".ts" form), because an
-//       SS-mode M=128 x N=128 MMA would need the full 128 B/clk of shared-memory bandwidth three times per k-step;
-//   issuers (lane 0 of warps 12-15, one k-step each)
-//     * a single thread can only issue one tcgen05.mma per ~200 clk (measured, scripts/bench_cu/mma_rate.cu) while
-//       a 128x128x8 tf32 MMA occupies the tensor pipe for 64: four issuers keep it fed (83 % of peak in isolation);
-//     * per chunk each issues 2 halves x 3 terms (lo*hi + hi*lo + hi*hi) and commits to the mbarriers that recycle
-//       the TMEM A stage / shared B stage; B (weights) is pre-split, pre-swizzled by wmd_pack_conv_weight_tc_f32
-//       into one [hi | lo] image per (n-tile, chunk): a single 32 KB cp.async.bulk into a 4-deep ring;
+//   gather warps (8-13)
+//     * implicit im2col by the TMA: `cp.async.bulk.tensor.2d...tile::gather4` fetches the 128-byte channel slice of
+//       four arbitrary source rows (indices from the per-tile tap table; row -1 = inactive / padded tap and the
+//       channel tail are zero-filled by the TMA) into a raw fp32, 128B-swizzled shared tile: 64 loads per chunk,
+//       three raw stages (two chunks in flight while one is being split), completion by mbarrier transaction bytes;
+//   split warps (0-7), thread = tile row = TMEM lane
+//     * read the row's 128 bytes back (the swizzle makes this transposed read conflict-free), split x = hi + lo
+//       (hi = x with the 13 low mantissa bits cleared, lo = x - hi: exact) and write hi / lo into TENSOR MEMORY with
+//       tcgen05.st - the MMAs take A from TMEM (".ts" form), because an SS-mode M=128 x N=128 MMA would need the
+//       full 128 B/clk of shared-memory bandwidth three times per k-step;
+//   issuers (warps 14-15, one per M half = one per accumulator)
+//     * whole warp in the loop, one elected lane issues: 4 k-steps x 3 terms (lo*hi + hi*lo + hi*hi) per chunk, then
+//       commits to the mbarriers that recycle the TMEM A stage / shared B stage.  B (weights) is pre-split,
+//       pre-swizzled by wmd_pack_conv_weight_tc_f32 into one [hi | lo] image per (n-tile, chunk): a single
+//       cp.async.bulk per chunk into a 3-deep ring;
 //   all 16 warps
 //     * the tensor core's fp32 accumulation rounds toward zero, a bias that grows linearly with K (measured
 //       ~6.5e-9 * K relative).  So accumulation runs in EPOCHS of kFlushChunks chunks: a finished epoch is drained
 //       (tcgen05.ld) into per-thread fp32 registers with round-to-nearest adds and the TMEM accumulators are
-//       re-zeroed.  Each thread ends up owning one output row x 64 channels: bias + activation + one 256-byte store.
-// TMEM map (512 columns): [0,256) accumulators (half h at h*128), [256,512) A operand: stage s, half h at
+//       re-zeroed.  Each thread ends up owning one output row x N/2 channels: bias + activation + one contiguous store.
+// What bounds it (scripts/tc_trace.py, scripts/bench_cu/*): shared-memory wavefronts.  Per chunk at N=128 the MMAs read
+// B 24 x 4 KB (768 wavefronts), B lands (256), raw A lands (256) and is read back (256): ~1540 clk against ~1620 clk of
+// tensor-pipe work.  The earlier cp.async gather cost ~640 wavefronts per chunk on top and serialised with the split.
+// TMEM map (512 columns): [0,2N) accumulators (half h at h*N), [256,512) A operand: stage s, half h at
 // 256 + s*128 + h*64, hi in the first 32 columns, lo in the next 32.
+#include <cuda.h>   // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
+
 #include "common.cuh"
 
 namespace wmd {
 
 constexpr int TC_BM = 256;                      // rows per CTA tile = 2 UMMA halves of 128
 constexpr int TC_BK = 32;                       // floats per chunk = one 128-byte swizzle-atom row
-constexpr int TC_THREADS = 512;                 // 16 warps: 12 producers + 4 issuers; all drain (lane quarter w&3, half (w>>2)&1, cols w>>3)
-constexpr int TC_PROD_WARPS = 12;
-constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
-constexpr int TC_A_STAGES = 2;                  // raw A tiles in shared memory (and split A stages in TMEM)
-constexpr int TC_B_STAGES = 4;                  // [Bhi | Blo] images in shared memory
+constexpr int TC_THREADS = 512;                 // 16 warps: 8 split + 6 gather + 2 issuers; all drain (lane quarter w&3, half (w>>2)&1, cols w>>3)
+constexpr int TC_SPLIT_WARPS = 8;               // warps 0-7: warp w owns tile rows (w>>2)*128 + (w&3)*32 + lane (its TMEM lane quarter)
+constexpr int TC_GATHER_WARPS = 6;              // warps 8-13
+constexpr int TC_ISSUERS = 2;                   // warps 14-15: one per M half, each the only writer of its accumulator
+constexpr int TC_A_STAGES = 3;                  // raw A tiles in shared memory (two gathers in flight + one being split)
+constexpr int TC_T_STAGES = 2;                  // split A stages in tensor memory
+constexpr int TC_B_STAGES = 3;                  // [Bhi | Blo] images in shared memory
 constexpr int TC_A_TILE = TC_BM * TC_BK * 4;    // 32 KB raw fp32
 constexpr int TC_TABLES = 2 * 9 * TC_BM * 4;
 constexpr int TC_TMEM_COLS = 512;
 
-// Per N-tile configuration.  A single thread issues one tcgen05.mma per ~200 clk whatever its size, so narrow
-// tiles need more issuers to keep the tensor pipe fed; every issuer gets a PRIVATE accumulator copy (one writer per
-// accumulator => the order of the round-toward-zero accumulations, and with it every output bit, is fixed) and the
-// copies are summed in registers at drain time.  Accumulators: (half h, copy j) at column (h*COPIES + j)*BN <= 256.
+// Per N-tile configuration.  Accumulators: M half h at TMEM column h*BN; each is written by exactly one issuer, so the
+// order of the round-toward-zero accumulations - and with it every output bit - is fixed.
 template <int BN>
 struct TcCfg {
-  static constexpr int COPIES = BN >= 128 ? 1 : 2;
-  static constexpr int ISSUERS = 2 * COPIES;               // issuer i: half i / COPIES, k-steps (i % COPIES) + n*COPIES
   static constexpr int B_TILE = BN * TC_BK * 4;            // bytes of one of hi / lo
   static constexpr int ACC = BN / 2;                       // accumulator registers per thread: its row x BN/2 columns
   static constexpr size_t SMEM = static_cast<size_t>(TC_A_STAGES) * TC_A_TILE +
                                  static_cast<size_t>(TC_B_STAGES) * 2 * B_TILE + TC_TABLES + 1024;
-  static_assert(2 * COPIES * BN <= 256, "accumulators must leave 256 TMEM columns for the A operand");
+  static_assert(2 * BN <= 256, "accumulators must leave 256 TMEM columns for the A operand");
 };
 constexpr int kFlushChunks = 32;                // epoch length: K = 1024 per TMEM accumulation run
-constexpr int kPrefetchAhead = 4;               // chunks of L2 prefetch distance
-constexpr uint32_t kNoRow = 0xFFFFFFFFu;        // tap-table entry of an inactive / padded source
+constexpr int32_t kNoRow = -1;                  // tap-table entry of an inactive / padded source: an out-of-bounds TMA row reads zeros
 
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -73,7 +77,7 @@ __device__ unsigned int g_dbg[4];
 #define MBAR_SPINS (1u << 28)
 #endif
 // -DWMD_TC_TRACE (scripts/tc_trace.py builds a separate library): CTA 0 records clock64() at fixed points of the
-// first kTraceChunks chunks for producer warp 0, producer warp 11 and issuer 0.
+// first kTraceChunks chunks for split warp 0, gather warp 8 and issuer 0.
 #ifdef WMD_TC_TRACE
 constexpr int kTraceChunks = 256, kTraceSlots = 8;
 __device__ long long g_trace[3 * kTraceSlots * kTraceChunks];
@@ -100,11 +104,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void producer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(TC_PROD_THREADS) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"); rows are 128 bytes, 8-row groups
 // are 1024 bytes apart (SBO), LBO is the canonical 1 for swizzled K-major operands.
@@ -149,6 +151,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
   const uint32_t z = 0u;
   asm volatile(
@@ -177,15 +186,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_conv_desc d, const float* __restrict__ wtc,
-                                                                     const int splits, float* __restrict__ partial) {
+                                                                     const int splits, float* __restrict__ partial,
+                                                                     const __grid_constant__ CUtensorMap tm0,
+                                                                     const __grid_constant__ CUtensorMap tm1) {
   using Cfg = TcCfg<BN>;
   constexpr int TC_B_TILE = Cfg::B_TILE;
-  constexpr int TC_ISSUERS = Cfg::ISSUERS;
-  constexpr int COPIES = Cfg::COPIES;
   constexpr int ACC = Cfg::ACC;
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) uint64_t bar_asplit[2];          // split A of the TMEM stage is stored (12 producer warps)
-  __shared__ __align__(8) uint64_t bar_mma[2];             // chunk's MMAs done (4 issuers): TMEM A stage + B stage reusable
+  __shared__ __align__(8) uint64_t bar_raw_full[TC_A_STAGES];   // raw A tile of the stage has landed (TMA transaction bytes)
+  __shared__ __align__(8) uint64_t bar_raw_empty[TC_A_STAGES];  // ... has been read by the 8 split warps
+  __shared__ __align__(8) uint64_t bar_asplit[TC_T_STAGES];     // split A of the TMEM stage is stored (8 split warps)
+  __shared__ __align__(8) uint64_t bar_mma[TC_T_STAGES];        // chunk's MMAs done (2 issuers): TMEM A stage + B stage reusable
   __shared__ __align__(8) uint64_t bar_b[TC_B_STAGES];     // weight image of the stage has landed (bulk copy)
   __shared__ __align__(8) uint64_t bar_epoch;              // accumulation epoch complete (4 issuers)
   __shared__ uint32_t tmem_base_slot;
@@ -193,16 +204,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   // warp index through a shuffle: provably warp-uniform, so the role branches and everything the issuer warps
   // compute from it stay on the uniform datapath (see the issuer section)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const bool is_producer = warp < TC_PROD_WARPS;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* sA_base = base;
   unsigned char* sB_base = base + TC_A_STAGES * TC_A_TILE;
-  uint32_t* tab0 = reinterpret_cast<uint32_t*>(sB_base + TC_B_STAGES * 2 * TC_B_TILE);   // 16-byte-unit offsets into x0
-  uint32_t* tab1 = tab0 + 9 * TC_BM;                                                      // ... into x1
+  int32_t* tab0 = reinterpret_cast<int32_t*>(sB_base + TC_B_STAGES * 2 * TC_B_TILE);   // [tap][row]: source row in x0, -1 = none
+  int32_t* tab1 = tab0 + 9 * TC_BM;                                                    // ... in x1
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bar_asplit[s]), TC_PROD_WARPS);
+    for (int s = 0; s < TC_A_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_raw_full[s]), 1);               // one expect_tx arrival; the gathers complete the bytes
+      mbar_init(smem_u32(&bar_raw_empty[s]), TC_SPLIT_WARPS);
+    }
+    for (int s = 0; s < TC_T_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_asplit[s]), TC_SPLIT_WARPS);
       mbar_init(smem_u32(&bar_mma[s]), TC_ISSUERS);
     }
     for (int s = 0; s < TC_B_STAGES; ++s) mbar_init(smem_u32(&bar_b[s]), 1);
@@ -231,7 +245,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   const long long tiles = static_cast<long long>((rows + TC_BM - 1) / TC_BM) * n_tiles;
   const int Hs = d.H >> d.shift0, Ws = d.W >> d.shift0;
   const bool aligned_rows = (d.taps == 1 && d.map0 == nullptr);
-  const uint32_t ld0q = static_cast<uint32_t>(d.ld0 >> 2), ld1q = static_cast<uint32_t>(d.ld1 >> 2);
   // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                               (static_cast<uint32_t>(128 >> 4) << 24);
@@ -240,15 +253,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   const int my_q = warp & 3, my_half = (warp >> 2) & 1, my_ch = warp >> 3;
   const int my_row = my_half * 128 + my_q * 32 + lane;          // row within the CTA tile
   const uint32_t lane_field = static_cast<uint32_t>(my_q * 32) << 16;
-  const uint32_t my_acc_addr = tmem_acc + lane_field + static_cast<uint32_t>(my_half * COPIES * BN + my_ch * ACC);
+  const uint32_t my_acc_addr = tmem_acc + lane_field + static_cast<uint32_t>(my_half * BN + my_ch * ACC);
   uint32_t mma_rounds = 0;                                       // chunks issued so far by this CTA (all tiles)
   uint32_t epochs = 0;                                           // epoch commits so far
 
   // accumulators start (and are left by every drain) at zero: every MMA accumulates
 #pragma unroll
-  for (int j = 0; j < COPIES; ++j)
-#pragma unroll
-    for (int cc = 0; cc < ACC; cc += 16) tmem_zero16(my_acc_addr + static_cast<uint32_t>(j * BN + cc));
+  for (int cc = 0; cc < ACC; cc += 16) tmem_zero16(my_acc_addr + static_cast<uint32_t>(cc));
   asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -297,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     for (int e = tid; e < d.taps * TC_BM; e += TC_THREADS) {
       const int tap = e / TC_BM, r = e - tap * TC_BM;
       const int m = m0 + r;
-      uint32_t o0 = kNoRow, o1 = kNoRow;
+      int32_t o0 = kNoRow, o1 = kNoRow;
       if (m < rows) {
         const int p = d.pixels ? d.pixels[m] : m;
         const int n = static_cast<int>(p / HW);
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           const int q = (n * d.H + qy) * d.W + qx;
           if (d.gate && !d.gate[q]) ok = false;
           if (ok) {
-            o1 = static_cast<uint32_t>(q) * ld1q;
+            o1 = q;
             int r0;
             if (aligned_rows) {
               r0 = m;
@@ -319,7 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
               const int qs = (n * Hs + (qy >> d.shift0)) * Ws + (qx >> d.shift0);
               r0 = d.map0 ? d.map0[qs] : qs;
             }
-            if (r0 >= 0) o0 = static_cast<uint32_t>(r0) * ld0q;
+            if (r0 >= 0) o0 = r0;
           }
         }
       }
@@ -339,121 +350,154 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     // drains this thread's slice (its row, ACC columns of every issuer's copy) with round-to-nearest adds, re-zeroes it
     auto drain = [&]() {
 #pragma unroll
-      for (int cp = 0; cp < COPIES; ++cp) {
+      for (int cc = 0; cc < ACC; cc += 16) {
+        uint32_t v[16];
+        tmem_ld16(my_acc_addr + static_cast<uint32_t>(cc), v);
 #pragma unroll
-        for (int cc = 0; cc < ACC; cc += 16) {
-          uint32_t v[16];
-          tmem_ld16(my_acc_addr + static_cast<uint32_t>(cp * BN + cc), v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[cc + j] += __uint_as_float(v[j]);
-          tmem_zero16(my_acc_addr + static_cast<uint32_t>(cp * BN + cc));
-        }
+        for (int j = 0; j < 16; ++j) acc[cc + j] += __uint_as_float(v[j]);
+        tmem_zero16(my_acc_addr + static_cast<uint32_t>(cc));
       }
       asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
     };
 
-    if (is_producer) {
-      // =================================================================================== producers
-      // decode chunk c -> gather source (as float4 pointer), channels left, offset table
-      auto chunk_src = [&](int c, const float4*& xq, int& cleft) -> const uint32_t* {
-        const int tap = c / per_tap;
-        const int rr = c - tap * per_tap;
-        const bool src1 = rr >= nch0;
-        const int ci0 = (src1 ? rr - nch0 : rr) * TC_BK;
-        cleft = (src1 ? d.c1 : d.c0) - ci0;
-        xq = reinterpret_cast<const float4*>(src1 ? d.x1 : d.x0) + (ci0 >> 2);
-        return (src1 ? tab1 : tab0) + tap * TC_BM;
-      };
-      auto prefetch_chunk = [&](int c) {
-        const float4* xq; int cleft;
-        const uint32_t* tab = chunk_src(c, xq, cleft);
-        if (tid < TC_BM) {                          // one 128-byte line per row
-          const uint32_t off = tab[tid];
-          if (off != kNoRow) prefetch_l2(xq + off);
-        }
-      };
-      // raw fp32 A tile of chunk c -> shared A stage c&1 (128B-swizzled rows); 2048 pieces over 384 threads
-      auto load_a = [&](int c, int st) {
-        const float4* xq; int cleft;
-        const uint32_t* tab = chunk_src(c, xq, cleft);
-        unsigned char* sA = sA_base + st * TC_A_TILE;
+    // epoch boundary (every role, top of chunk c): the accumulation run that ended with chunk c-1 is drained by all
+    // 16 warps before any MMA of chunk c is issued
+    auto epoch_boundary = [&](int c) {
+      if ((c % kFlushChunks) == 0 && c > 0) {
+        mbar_wait(smem_u32(&bar_epoch), (epochs - 1) & 1, 0x10000u + round0 + c);
+        tc_fence_after();
+        drain();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+      }
+    };
+
+    // Implicit im2col through the TMA: every `tile::gather4` load fetches the 128-byte channel slice of FOUR arbitrary
+    // source rows (row indices from the tap table; -1 and channels past C are zero-filled by the TMA) into 512
+    // contiguous, 128B-swizzled bytes of the raw stage and completes on the stage's mbarrier.  A chunk is 64 loads:
+    // gather warp g issues groups g, g+6, ...  One load costs the issuing warp ~140 clk here - that is the TMA unit's
+    // queue, not the warp: the unit sustains one gather4 per ~25-30 clk per SM next to the weight copies, i.e. the
+    // L2->SM path at ~9 TB/s aggregate (A 32 KB + B <= 32 KB per chunk per SM).  Letting the split warps issue part
+    // of the loads (kSplitGather > 0) was measured and does not help.  Everything a load needs except the four row
+    // indices is made provably warp-uniform (shuffles), so ptxas keeps it in uniform registers across the unrolled
+    // loop; per load that leaves one LDS.128 + four R2URs.
+    constexpr int kMaxLoadsPerWarp = (TC_BM / 4 + TC_GATHER_WARPS - 1) / TC_GATHER_WARPS;
+    const uint32_t sA_u = __shfl_sync(0xffffffffu, smem_u32(sA_base), 0);
+    auto issue_gathers = [&](int c, uint32_t round, int g0, int gstride, int gend, int nmax, bool expect) {
+      const uint32_t st = round % TC_A_STAGES;
+      const int rr = c / d.taps;                  // channel chunk outermost, taps innermost: the nine taps of a
+      const int tap = c - rr * d.taps;            // chunk re-read (almost) the same rows while they are hot in L2
+      const bool src1 = rr >= nch0;
+      const int col = __shfl_sync(0xffffffffu, (src1 ? rr - nch0 : rr) * TC_BK, 0);
+      const uint32_t tab_u = __shfl_sync(0xffffffffu, smem_u32((src1 ? tab1 : tab0) + tap * TC_BM + 4 * g0), 0);
+      const uint64_t tmp = reinterpret_cast<uint64_t>(src1 ? &tm1 : &tm0);
+      const uint64_t tm_u = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp >> 32), 0)) << 32) |
+                            __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp), 0);
+      const uint32_t bar = __shfl_sync(0xffffffffu, smem_u32(&bar_raw_full[st]), 0);
+      const uint32_t dst_u = __shfl_sync(0xffffffffu, sA_u + st * TC_A_TILE + g0 * 512, 0);
+      if (expect && elect_one())
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(static_cast<uint32_t>(TC_A_TILE)) : "memory");
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const int p = tid + i * TC_PROD_THREADS;
-          if (p < TC_BM * 8) {
-            const int r = p >> 3, j = p & 7;
-            const int a_bytes = max(0, min(16, (cleft - j * 4) * 4));
-            const uint32_t off = tab[r];
-            const bool live = off != kNoRow && a_bytes > 0;
-            const float4* src = live ? xq + off + j : xq;
-            cp_async16(sA + r * 128 + ((j ^ (r & 7)) << 4), src, live ? a_bytes : 0);
-          }
+      for (int i = 0; i < kMaxLoadsPerWarp; ++i) {
+        if (i < nmax && g0 + i * gstride < gend) {
+          int4 r4;
+          asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n"
+              : "=r"(r4.x), "=r"(r4.y), "=r"(r4.z), "=r"(r4.w)
+              : "r"(tab_u + static_cast<uint32_t>(i * gstride * 16)));
+          if (elect_one())
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(
+                    dst_u + static_cast<uint32_t>(i * gstride * 512)),
+                "l"(tm_u), "r"(col), "r"(r4.x), "r"(r4.y), "r"(r4.z), "r"(r4.w), "r"(bar)
+                : "memory");
         }
-      };
+      }
+    };
+    constexpr int kSplitGather = 0;                                     // loads per split warp per chunk
+    constexpr int kGatherGroups = TC_BM / 4 - TC_SPLIT_WARPS * kSplitGather;   // groups left to the gather warps
+    static_assert(kGatherGroups <= kMaxLoadsPerWarp * TC_GATHER_WARPS, "issue_gathers unroll bound");
+    auto gather_chunk = [&](int c, uint32_t round) {                    // gather-warp share
+      issue_gathers(c, round, warp - TC_SPLIT_WARPS, TC_GATHER_WARPS, kGatherGroups, kMaxLoadsPerWarp, warp == TC_SPLIT_WARPS);
+    };
+    auto split_gather_chunk = [&](int c, uint32_t round) {              // split-warp share
+      issue_gathers(c, round, kGatherGroups + warp, TC_SPLIT_WARPS, TC_BM / 4, kSplitGather, false);
+    };
 
-      for (int c = 1; c <= kPrefetchAhead && c < len; ++c) prefetch_chunk(cb + c);
-      load_a(cb, 0);
-      cp_async_commit();
-
-      const int wt = warp >> 2;                      // 0..2: which of the quarter's three producer warps
+    if (warp < TC_SPLIT_WARPS) {
+      // =================================================================================== split warps
+      // raw fp32 row (128 B of the smem stage) -> hi / lo in tensor memory.  Thread = tile row `my_row` = TMEM lane.
+      if (kSplitGather > 0) {
+        split_gather_chunk(cb, round0);
+        if (len > 1) split_gather_chunk(cb + 1, round0 + 1);
+      }
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
-        const uint32_t tstage = round & 1;
-        const int trole = warp == 0 ? 0 : (warp == TC_PROD_WARPS - 1 ? 1 : 3);
-        if (trole < 3) TC_TRACE(trole, 0, c);
-        cp_async_wait<0>();
-        if (trole < 3) TC_TRACE(trole, 1, c);
-        producer_barrier();                          // raw A tile of chunk c complete; split reads of chunk c-1 done
-        if (trole < 3) TC_TRACE(trole, 2, c);
-        if (c + 1 < len) {
-          load_a(cb + c + 1, (c + 1) & 1);
-          if (c + 1 + kPrefetchAhead < len) prefetch_chunk(cb + c + 1 + kPrefetchAhead);
+        const uint32_t rs = round % TC_A_STAGES, ts = round & 1;
+        epoch_boundary(c);
+        if (kSplitGather > 0 && c + 2 < len) {       // my share of the gather two chunks ahead (stage read by round-1: all 8 split warps done?)
+          const uint32_t r2 = round + 2, st2 = r2 % TC_A_STAGES;
+          if (c + 2 >= TC_A_STAGES) mbar_wait(smem_u32(&bar_raw_empty[st2]), ((r2 - TC_A_STAGES) / TC_A_STAGES) & 1, 0x38000u + round);
+          split_gather_chunk(cb + c + 2, r2);
         }
-        cp_async_commit();
-        if (trole < 3) TC_TRACE(trole, 3, c);
-        if ((c % kFlushChunks) == 0 && c > 0) {      // epoch boundary: everybody drains before the next epoch starts
-          mbar_wait(smem_u32(&bar_epoch), (epochs - 1) & 1, 0x10000u + round);
-          tc_fence_after();
-          drain();
-          tc_fence_before();
-          __syncthreads();
-          tc_fence_after();
-        }
+        if (warp == 0) TC_TRACE(0, 0, c);
+        mbar_wait(smem_u32(&bar_raw_full[rs]), (round / TC_A_STAGES) & 1, 0x20000u + round);
+        if (warp == 0) TC_TRACE(0, 1, c);
         // TMEM A stage free?  It was read by the MMAs of round-2.
-        if (round >= 2) mbar_wait(smem_u32(&bar_mma[tstage]), ((round - 2) >> 1) & 1, 0x20000u + round);
+        if (round >= 2) mbar_wait(smem_u32(&bar_mma[ts]), ((round - 2) >> 1) & 1, 0x28000u + round);
         tc_fence_after();
-        if (trole < 3) TC_TRACE(trole, 4, c);
-        // split my (row, 8 channels) slots: u = half*4 + channel-quarter, u = wt, wt+3, wt+6
-        {
-          const unsigned char* tile_a = sA_base + (c & 1) * TC_A_TILE;
+        if (warp == 0) TC_TRACE(0, 2, c);
+        const unsigned char* rowp = sA_base + rs * TC_A_TILE + my_row * 128;
+        const uint32_t ta = tmem_acc + lane_field + 256u + ts * 128u + static_cast<uint32_t>(my_half * 64);
 #pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            const int slot = wt + 3 * u;
-            if (slot < 8) {
-              const int h = slot >> 2, kq = slot & 3;
-              const int r = h * 128 + my_q * 32 + lane;
-              const unsigned char* rowp = tile_a + r * 128;
-              const uint4 v0 = *reinterpret_cast<const uint4*>(rowp + (((2 * kq) ^ (r & 7)) << 4));
-              const uint4 v1 = *reinterpret_cast<const uint4*>(rowp + (((2 * kq + 1) ^ (r & 7)) << 4));
-              const uint32_t raw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-              uint32_t hi[8], lo[8];
+        for (int hf = 0; hf < 2; ++hf) {              // 16 channels at a time
+          uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                hi[e] = raw[e] & 0xFFFFE000u;                                       // tf32 by truncation
-                lo[e] = __float_as_uint(__uint_as_float(raw[e]) - __uint_as_float(hi[e]));   // exact remainder
-              }
-              const uint32_t ta = tmem_acc + lane_field + 256u + tstage * 128u + static_cast<uint32_t>(h * 64 + kq * 8);
-              tmem_st8(ta, hi);
-              tmem_st8(ta + 32u, lo);
+          for (int q = 0; q < 4; ++q) {
+            const uint4 v = *reinterpret_cast<const uint4*>(rowp + (((4 * hf + q) ^ (my_row & 7)) << 4));   // swizzle: conflict-free
+            const uint32_t raw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[4 * q + e] = raw[e] & 0xFFFFE000u;                                                    // tf32 by truncation
+              lo[4 * q + e] = __float_as_uint(__uint_as_float(raw[e]) - __uint_as_float(hi[4 * q + e]));   // exact remainder
             }
           }
-          if (trole < 3) TC_TRACE(trole, 5, c);
-          asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+          tmem_st16(ta + static_cast<uint32_t>(16 * hf), hi);
+          tmem_st16(ta + 32u + static_cast<uint32_t>(16 * hf), lo);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_raw_empty[rs]));      // raw stage may be overwritten
+        if (warp == 0) TC_TRACE(0, 3, c);
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar_asplit[tstage]));
-        if (trole < 3) TC_TRACE(trole, 6, c);
+        if (lane == 0) mbar_arrive(smem_u32(&bar_asplit[ts]));
+        if (warp == 0) TC_TRACE(0, 4, c);
+        if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
+      }
+    } else if (warp < TC_SPLIT_WARPS + TC_GATHER_WARPS) {
+      // =================================================================================== gather warps
+      // Implicit im2col through the TMA: every `tile::gather4` load fetches the 128-byte channel slice of FOUR
+      // arbitrary source rows (row indices from the tap table; -1 and channels past C are zero-filled by the TMA)
+      // into 512 contiguous, 128B-swizzled bytes of the raw stage and completes on the stage's mbarrier.
+      // 64 loads per chunk, dealt round-robin to the gather warps; the LSU is not involved (a cp.async gather costs
+      // ~10 shared-memory wavefronts per instruction and made the kernel shared-memory bound).
+      // the raw stages are free at the start of a tile (every split of the previous tile has completed)
+      gather_chunk(cb, round0);
+      if (len > 1) gather_chunk(cb + 1, round0 + 1);
+      for (int c = 0; c < len; ++c) {
+        const uint32_t round = round0 + c;
+        epoch_boundary(c);
+        if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 0, c);
+        if (c + 2 < len) {
+          const uint32_t r2 = round + 2, st2 = r2 % TC_A_STAGES;
+          // stage st2 was last filled for round r2-3: wait until the split warps have read it
+          if (c + 2 >= TC_A_STAGES) mbar_wait(smem_u32(&bar_raw_empty[st2]), ((r2 - TC_A_STAGES) / TC_A_STAGES) & 1, 0x30000u + round);
+          if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 1, c);
+          gather_chunk(cb + c + 2, r2);
+        }
+        if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 2, c);
+        if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 3, c);
         if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
       }
     } else {
@@ -462,10 +506,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       // operands derived from warp-uniform values) ptxas keeps the MMA operands in uniform registers and emits the
       // UTCHMMAs back to back: ~78 clk per instruction.  A `lane == 0` branch instead makes it wrap every MMA in an
       // ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~210 clk (scripts/bench_cu/mma_rate*.cu).
-      const int kstep = warp - TC_PROD_WARPS;        // this issuer's index
+      const int ih = warp - (TC_SPLIT_WARPS + TC_GATHER_WARPS);     // this issuer's M half = its accumulator
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_acc, 0);
       const uint32_t sB_u = __shfl_sync(0xffffffffu, smem_u32(sB_base), 0);
-      if (kstep == 0 && elect_one()) {
+      if (ih == 0 && elect_one()) {
         const unsigned char* w0 = wtile + static_cast<long long>(cb) * (2 * TC_B_TILE);
         bulk_g2s(sB_u + (round0 % TC_B_STAGES) * 2 * TC_B_TILE, w0, 2 * TC_B_TILE, smem_u32(&bar_b[round0 % TC_B_STAGES]));
         if (len > 1)
@@ -473,56 +517,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
                    smem_u32(&bar_b[(round0 + 1) % TC_B_STAGES]));
       }
       __syncwarp();
-      // issuer -> (M half, accumulator copy); it alone writes that accumulator
-      const int ih = kstep / COPIES, icp = kstep % COPIES;
-      const uint32_t dh = tmem_u + static_cast<uint32_t>((ih * COPIES + icp) * BN);
+      const uint32_t dh = tmem_u + static_cast<uint32_t>(ih * BN);
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
-        const uint32_t tstage = round & 1;
+        const uint32_t ts = round & 1;
         const uint32_t bs = round % TC_B_STAGES;
-        if ((c % kFlushChunks) == 0 && c > 0) {      // epoch boundary (all lanes: drain is warp-collective)
-          mbar_wait(smem_u32(&bar_epoch), (epochs - 1) & 1);
-          tc_fence_after();
-          drain();
-          tc_fence_before();
-          __syncthreads();
-          tc_fence_after();
-        }
-        if (kstep < TC_ISSUERS) {
-          if (kstep == 0) TC_TRACE(2, 0, c);
-          mbar_wait(smem_u32(&bar_asplit[tstage]), (round >> 1) & 1, 0x30000u + round);           // split A of this chunk is in TMEM
-          if (kstep == 0) TC_TRACE(2, 1, c);
-          mbar_wait(smem_u32(&bar_b[bs]), (round / TC_B_STAGES) & 1, 0x40000u + round);           // weight image has landed
-          if (kstep == 0) TC_TRACE(2, 2, c);
-          tc_fence_after();
-          const uint64_t b0 = umma_desc_sw128(sB_u + bs * 2 * TC_B_TILE);
-          const uint32_t ah = tmem_u + 256u + tstage * 128u + static_cast<uint32_t>(ih * 64);
-          if (elect_one()) {
+        epoch_boundary(c);
+        if (ih == 0) TC_TRACE(2, 0, c);
+        mbar_wait(smem_u32(&bar_asplit[ts]), (round >> 1) & 1, 0x40000u + round);           // split A of this chunk is in TMEM
+        if (ih == 0) TC_TRACE(2, 1, c);
+        mbar_wait(smem_u32(&bar_b[bs]), (round / TC_B_STAGES) & 1, 0x48000u + round);        // weight image has landed
+        if (ih == 0) TC_TRACE(2, 2, c);
+        tc_fence_after();
+        const uint64_t b0 = umma_desc_sw128(sB_u + bs * 2 * TC_B_TILE);
+        const uint32_t ah = tmem_u + 256u + ts * 128u + static_cast<uint32_t>(ih * 64);
+        if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < TC_BK / 8; ++ks) {
-              if ((ks % COPIES) == icp) {
-                const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
-                const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
-                const uint32_t a = ah + static_cast<uint32_t>(8 * ks);
-                umma_tf32_ts(dh, a + 32u, bh, kIdesc, 1u);     // lo*hi
-                umma_tf32_ts(dh, a, bl, kIdesc, 1u);           // hi*lo
-                umma_tf32_ts(dh, a, bh, kIdesc, 1u);           // hi*hi
-              }
-            }
-            umma_commit(smem_u32(&bar_mma[tstage]));
-            if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) umma_commit(smem_u32(&bar_epoch));
-            // weights two chunks ahead: that B stage was last read by round-2, and all of round-2's MMAs are known to
-            // be complete - the producers only stored this chunk's A (bar_asplit, awaited above) after bar_mma(round-2).
-            // (Waiting on bar_mma here would alias: this round's own commits may already have flipped its phase.)
-            if (kstep == 0 && c + 2 < len) {
-              const uint32_t ns = (round + 2) % TC_B_STAGES;
-              bulk_g2s(sB_u + ns * 2 * TC_B_TILE, wtile + static_cast<long long>(cb + c + 2) * (2 * TC_B_TILE),
-                       2 * TC_B_TILE, smem_u32(&bar_b[ns]));
-            }
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
+            const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
+            const uint32_t a = ah + static_cast<uint32_t>(8 * ks);
+            umma_tf32_ts(dh, a + 32u, bh, kIdesc, 1u);     // lo*hi
+            umma_tf32_ts(dh, a, bl, kIdesc, 1u);           // hi*lo
+            umma_tf32_ts(dh, a, bh, kIdesc, 1u);           // hi*hi
+          }
+          umma_commit(smem_u32(&bar_mma[ts]));
+          if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) umma_commit(smem_u32(&bar_epoch));
+          // weights two chunks ahead go into the stage chunk c-1 used: wait for that chunk's MMAs.  This costs
+          // nothing - chunk c's MMAs are queued behind them and chunk c+1's A cannot be split before they finish
+          // either (TMEM stage).  No phase aliasing: bar_mma[(round-1)&1] next completes for round+1, which needs
+          // this thread's own commit.
+          if (ih == 0 && c + 2 < len) {
+            if (c >= 1) mbar_wait(smem_u32(&bar_mma[(round - 1) & 1]), ((round - 1) >> 1) & 1, 0x50000u + round);
+            const uint32_t ns = (round + 2) % TC_B_STAGES;
+            bulk_g2s(sB_u + ns * 2 * TC_B_TILE, wtile + static_cast<long long>(cb + c + 2) * (2 * TC_B_TILE),
+                     2 * TC_B_TILE, smem_u32(&bar_b[ns]));
           }
         }
         __syncwarp();
-        if (kstep == 0) TC_TRACE(2, 3, c);
+        if (ih == 0) TC_TRACE(2, 3, c);
         if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
       }
     }
@@ -580,7 +613,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
 }
 
 // w (Cout, Cin, taps) fp32 -> per (n-tile, chunk) smem image [tf32 hi: BN x 32 | tf32 lo: BN x 32], K-major,
-// 128B-swizzled.  Chunk order = the kernel's: tap-major, then source-0 channel chunks, then source-1 chunks.
+// 128B-swizzled.  Chunk order = the kernel's: source-0 channel chunks then source-1 chunks, the taps of a chunk innermost.
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int c0, int c1,
                                       int taps, int BN, long long total) {
   const int nch0 = (c0 + TC_BK - 1) / TC_BK, nch1 = (c1 + TC_BK - 1) / TC_BK;
@@ -597,8 +630,8 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
     const int hilo = static_cast<int>(t % 2); t /= 2;
     const int c = static_cast<int>(t % nchunks);
     const int nt = static_cast<int>(t / nchunks);
-    const int tap = c / per_tap;
-    const int rr = c - tap * per_tap;
+    const int rr = c / taps;
+    const int tap = c - rr * taps;
     const bool src1 = rr >= nch0;
     const int ci_local = (src1 ? rr - nch0 : rr) * TC_BK + kk;
     const int csrc = src1 ? c1 : c0;
@@ -671,9 +704,44 @@ __global__ void tc_reduce_kernel(const float* __restrict__ partial, int splits, 
 
 static int tc_tile_n(int cout) { return cout >= 96 ? 128 : (cout >= 48 ? 64 : 32); }
 
+// TMA descriptor of a source: 2-D fp32 tensor [rows][C] with row pitch ld floats, box = one row x 32 channels,
+// 128-byte swizzle, zero fill outside (inactive taps are row -1; a channel tail reads zeros)
+typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_rows_map(CUtensorMap* tm, const float* x, int C, long long rows, int ld) {
+  static TmEncodeFn encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return WMD_ERR_UNSUPPORTED;
+    encode = reinterpret_cast<TmEncodeFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(rows < 1 ? 1 : rows)};
+  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {TC_BK, 1}, estr[2] = {1, 1};
+  const CUresult rc = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? WMD_OK : WMD_ERR_UNSUPPORTED;
+}
+
 template <int BN>
 static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
+  CUtensorMap tm0, tm1;
+  {
+    const long long px = static_cast<long long>(d.N) * d.H * d.W;
+    const long long rows0 = static_cast<long long>(d.N) * (d.H >> d.shift0) * (d.W >> d.shift0);
+    int rc = make_rows_map(&tm0, d.x0, d.c0, rows0, d.ld0);
+    if (rc != WMD_OK) return rc;
+    if (d.c1 > 0) {
+      rc = make_rows_map(&tm1, d.x1, d.c1, px, d.ld1);
+      if (rc != WMD_OK) return rc;
+    } else {
+      tm1 = tm0;
+    }
+  }
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -686,7 +754,7 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN) * (splits > 0 ? splits : 1);
   const long long cap = sm_count();
   const int grid = splits == 0 ? static_cast<int>(cap) : static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
-  conv_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial);
+  conv_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial, tm0, tm1);
   int rc = launched();
   if (rc != WMD_OK || splits == 1) return rc;
   const int nchunks = d.taps * ((d.c0 + TC_BK - 1) / TC_BK + (d.c1 + TC_BK - 1) / TC_BK);
