@@ -210,8 +210,8 @@ def roofline_from(records, peak_gbs, peak_tf, peak_src, steps):
                 "hbm_view": {"achieved_gbs": hbm_view["achieved"], "peak_gbs": peak_gbs, "frac": hbm_view["frac"]},
                 "peak_source": peak_src + ": bf16_tflops / 2 for tf32",
                 "note": "tcgen05.mma.kind::tf32, 3 MMAs per fp32 product (hi*hi + hi*lo + lo*hi), fp32 accumulation in "
-                        "TMEM; one issuing thread sustains one MMA per ~200 clk, so with one writer per accumulator "
-                        "(deterministic) the 128x128x8 tiles cap the pipe at ~64 % (DESIGN.md 4)"}
+                        "TMEM; A gathered by TMA gather4 and moved to TMEM by split warps; the N=128 layers run at "
+                        "~0.8 of this peak, the N<=64 layers are bound by the gather (L2->SM path), see DESIGN.md 4"}
     else:
         main = dict(hbm_view)
         main.update(kernel=dom, peak_source=peak_src,
@@ -349,7 +349,7 @@ def time_device(step_fn, steps, warmup, dist, world):
 
 def run_native(args, rank, world, local_rank):
     import torch.distributed as dist
-    from wavelet_monodepth_b200 import _lib, ops, shard
+    from wavelet_monodepth_b200 import _lib, graphs, ops, shard
     from wavelet_monodepth_b200.kitti_decoders import SparseDepthWaveProgressiveDecoder
 
     torch.cuda.set_device(local_rank)
@@ -374,8 +374,21 @@ def run_native(args, rank, world, local_rank):
     resident = [f.to(dev) for f in host]
     last = {}
 
-    def step():
+    def step_eager():
         out = dec(resident, THRESH)
+        if world > 1:
+            last["gathered"] = shard.all_gather_batch(out[("disp", 0)], n_global)
+        last["out"] = out
+
+    # serving mode: the ~70 launches of one forward captured once in a CUDA graph bound to the resident feature tensors
+    # (graphs.py); replay = the same kernels without the per-launch host cost.  --no-graph times the eager calls instead.
+    use_graph = not args.no_graph
+    graph = graphs.GraphedSparseDecoder(dec, resident, THRESH) if use_graph else None
+
+    def step():
+        if not use_graph:
+            return step_eager()
+        out = graph.replay()                                        # incl. the total_ops count read-back
         if world > 1:
             last["gathered"] = shard.all_gather_batch(out[("disp", 0)], n_global)
         last["out"] = out
@@ -392,6 +405,10 @@ def run_native(args, rank, world, local_rank):
     ms = time_device(step, args.steps, 1 if args.warmup else 0, dist, world)
     launches = _lib.launch_count() - l0
     launches -= (1 if args.warmup else 0) * (launches // (args.steps + (1 if args.warmup else 0)))
+    if use_graph:
+        launches = graph.launches * args.steps                       # kernel nodes replayed inside the timed region
+    ms_eager = time_device(step_eager, args.steps, 1, dist, world) if use_graph else ms
+    value_eager = n_global * args.steps / (ms_eager * 1e-3)
     out = last["out"]
     dens = {s: round(float(out[("wavelet_mask", s)].float().mean()), 4) for s in (3, 2, 1, 0)}
     ops_per_frame = out["total_ops"] / n_local
@@ -401,14 +418,17 @@ def run_native(args, rank, world, local_rank):
     # the decoder then uses them in place and the five NCHW->rows transposes disappear
     resident_cl = [f.contiguous(memory_format=torch.channels_last) for f in resident]
 
+    graph_cl = graphs.GraphedSparseDecoder(dec, resident_cl, THRESH) if use_graph else None
+
     def step_cl():
-        o = dec(resident_cl, THRESH)
+        o = graph_cl.replay() if use_graph else dec(resident_cl, THRESH)
         if world > 1:
             shard.all_gather_batch(o[("disp", 0)], n_global)
 
     ms_cl = time_device(step_cl, args.steps, 2, dist, world)
     value_cl = n_global * args.steps / (ms_cl * 1e-3)
-    del resident_cl
+    del graph_cl, resident_cl
+    torch.cuda.empty_cache()
 
     # ---- 2. end to end: host features -> H2D (copy stream, double buffered) -> decode -> D2H of disp0
     copy_stream = torch.cuda.Stream()
@@ -418,6 +438,7 @@ def run_native(args, rank, world, local_rank):
     h2d_bytes = sum(f.numel() * 4 for f in host)
     d2h_bytes = disp_host.numel() * 4 + 9 * (n_local + 1) * 4
     state = {"i": 0}
+    graphs_e2e = [graphs.GraphedSparseDecoder(dec, b, THRESH) for b in bufs] if use_graph else None
 
     def enqueue_copy(slot):
         with torch.cuda.stream(copy_stream):
@@ -430,7 +451,7 @@ def run_native(args, rank, world, local_rank):
         slot = i % 2
         enqueue_copy(1 - slot)                                   # next step's inputs overlap this step's compute
         torch.cuda.current_stream().wait_event(ready[slot])
-        o = dec(bufs[slot], THRESH)                              # ends with the count read-back (host sync)
+        o = graphs_e2e[slot].replay() if use_graph else dec(bufs[slot], THRESH)   # ends with the count read-back (host sync)
         if world > 1:
             shard.all_gather_batch(o[("disp", 0)], n_global)
         disp_host.copy_(o[("disp", 0)], non_blocking=True)
@@ -441,7 +462,8 @@ def run_native(args, rank, world, local_rank):
     e2e_ms = time_device(e2e_step, args.steps, 2, dist, world)
     e2e_value = n_global * args.steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if sampler else None
-    del bufs
+    del graphs_e2e, bufs
+    torch.cuda.empty_cache()
 
     # ---- 3. per-kernel roofline pass (same workload, CUDA events around every libwmd launch)
     prof_steps = 3
@@ -463,8 +485,10 @@ def run_native(args, rank, world, local_rank):
         res2 = [f.to(dev) for f in host2]
         n2 = wl2["per_gpu_batch"] * world
 
+        graph2 = graphs.GraphedSparseDecoder(dec2, res2, THRESH) if use_graph else None
+
         def step2():
-            o = dec2(res2, THRESH)
+            o = graph2.replay() if use_graph else dec2(res2, THRESH)
             if world > 1:
                 shard.all_gather_batch(o[("disp", 0)], n2)
             last["out2"] = o
@@ -505,7 +529,10 @@ def run_native(args, rank, world, local_rank):
                 "features": "seeded blocky maps, cell %d px, texture %.2f" % (SYNTH["cell"], SYNTH["texture"]),
                 "timed_region": "decoder forward on NCHW fp32 features resident in HBM, incl. layout transposes, "
                                 "mask/compaction, the total_ops count read-back and (N>1) the all-gather",
+                "launch_mode": "CUDA graph replay (graphs.GraphedSparseDecoder)" if use_graph else "eager",
             },
+            "value_eager": {"value": round(value_eager, 1), "unit": UNIT, "ms_per_step": round(ms_eager / args.steps, 3),
+                            "note": "same step issued launch by launch from Python (no CUDA graph)"},
             "value_channels_last": {"value": round(value_cl, 1), "unit": UNIT, "ms_per_step": round(ms_cl / args.steps, 3),
                                     "note": "same step, encoder features in torch.channels_last: used zero-copy, no layout transposes"},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
@@ -528,6 +555,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=MAIN, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-frames", type=int, default=48)

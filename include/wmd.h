@@ -181,10 +181,11 @@ int wmd_conv_rows_tc_f32(const wmd_conv_desc* d, wmd_stream_t stream);
 /* Same, with the reduction split `splits` ways across CTAs (split-K): layers with few output tiles then fill all
  * SMs.  Partial sums go to `ws` (wmd_conv_tc_splitk_ws_bytes) and are summed in a fixed order, biased and
  * activated by a second small kernel, so results stay deterministic.  splits = 1 is wmd_conv_rows_tc_f32.
- * splits = 0 selects BALANCED scheduling: the (tile, 32-channel chunk) units are dealt to the CTAs in equal
- * contiguous ranges computed on the device from the actual row count (stream-K style), so sparse layers whose tile
- * count is data dependent still finish on all SMs together; tiles cut by a range boundary (<= 4 segments) go through
- * the same workspace + fixed-order reduce pass. */
+ * splits = 0 selects BALANCED scheduling (data-parallel + stream-K): full rounds of tiles run whole; the (tile,
+ * 32-channel chunk) units of the remainder tiles are dealt to the CTAs in equal contiguous ranges computed on the
+ * device from the actual row count, so sparse layers whose tile count is data dependent still finish on all SMs
+ * together; only remainder tiles cut by a range boundary (<= 8 segments) go through the workspace + fixed-order
+ * reduce pass.  Its workspace size does not depend on the layer (SMs x 8 x 256 x 128 floats). */
 size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits);
 int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* d, int splits, void* ws, size_t ws_bytes, wmd_stream_t stream);
 

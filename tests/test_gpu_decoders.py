@@ -285,3 +285,33 @@ def test_full_res_consumer_epilogue_matches_trainer_interpolate():
         want = F.interpolate(out[("disp", s)], mod.full_res_size, mode="bilinear", align_corners=False)
         assert float((out[("disp_full", s)] - want).abs().max()) <= 2e-6
     assert ("disp_full", 0) not in out
+
+
+def test_cuda_graph_replay_matches_eager_and_follows_input_updates():
+    """graphs.GraphedSparseDecoder: same kernels captured once; replay == eager bit for bit, also after the bound
+    input tensors are overwritten in place (what a graphed encoder does)."""
+    from wavelet_monodepth_b200 import graphs
+    mod, _, feats = _full_kitti(synth.RESNET18_CH, 4, 192, 640)
+    feats = [f.clone() for f in feats]
+    eager = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in mod(feats, 0.05).items()}
+    g = graphs.GraphedSparseDecoder(mod, feats, 0.05)
+    assert g.launches > 40 and g.bound_to(feats) and not g.bound_to([f.clone() for f in feats])
+    out = g.replay()
+    assert set(out) == set(eager)
+    for k, v in eager.items():
+        if torch.is_tensor(v):
+            assert torch.equal(out[k], v), key_str(k)
+        else:
+            assert out[k] == v, key_str(k)
+    # new content in the same tensors
+    torch.manual_seed(7)
+    for f in feats:
+        f.mul_(0.5).add_(0.1 * torch.rand_like(f))
+    ref = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in mod(feats, 0.05).items()}
+    out = g.replay()
+    for k, v in ref.items():
+        if torch.is_tensor(v):
+            assert torch.equal(out[k], v), key_str(k)
+        else:
+            assert out[k] == v, key_str(k)
+    assert not torch.equal(ref[("disp", 0)], eager[("disp", 0)])

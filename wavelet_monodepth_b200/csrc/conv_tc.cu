@@ -184,6 +184,30 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       : "memory");
 }
 
+// Balanced mode plan, shared by the conv kernel and the reduce pass (both derive it from the device-side row count).
+// All but the last full round of tiles run data-parallel (whole tiles); the last full round and the partial round
+// after it - between 1 and 2 x CTAs - 1 tiles - are cut stream-K style into equal ranges of U units per CTA.  Merging
+// the last full round in keeps the ranges long (>= one tile's reduction), so a tile has <= 2 segments; only when
+// there is no full round at all (fewer tiles than CTAs) the ranges are shorter: U >= nchunks/6, <= 7 segments.
+constexpr int kBalSlabs = 8;                    // workspace slabs: CTAs x kBalSlabs tiles of 256 x N floats
+struct BalPlan {
+  long long rem_tile0;                          // first stream-K tile
+  long long U;                                  // units (chunks) per CTA
+  int slabs;                                    // workspace slabs per stream-K tile
+};
+__host__ __device__ __forceinline__ BalPlan bal_plan(long long tiles, long long grid, int nchunks) {
+  BalPlan p;
+  const long long rounds = tiles / grid;
+  const long long dp_rounds = (tiles % grid == 0) ? rounds : (rounds > 0 ? rounds - 1 : 0);
+  p.rem_tile0 = dp_rounds * grid;
+  const long long rem_tiles = tiles - p.rem_tile0;
+  const long long even = (rem_tiles * nchunks + grid - 1) / grid;
+  const long long floor_u = (nchunks + 5) / 6;
+  p.U = even > floor_u ? even : floor_u;
+  p.slabs = rem_tiles >= grid ? 3 : kBalSlabs;  // rem_tiles * slabs <= grid * kBalSlabs either way (rem_tiles < 2 * grid)
+  return p;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_conv_desc d, const float* __restrict__ wtc,
                                                                      const int splits, float* __restrict__ partial,
@@ -267,28 +291,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
 
   // Work decomposition.  A "unit" is one 32-channel chunk of one output tile.
   //   splits >= 1 : every tile's reduction is cut into `splits` equal ranges (split-K); splits == 1 = whole tiles.
-  //   splits == 0 : BALANCED - the tiles x nchunks units are dealt out to the CTAs in equal contiguous ranges of U
-  //                 units (stream-K style), so the SMs finish together however many tiles the (device-side) row
-  //                 count yields.  A tile cut by a range boundary has <= 4 segments (U >= nchunks/3).
-  // Segments that do not cover a whole tile write raw partial sums to workspace slab `slab`; tc_reduce_kernel sums
-  // the slabs in a fixed order and applies bias + activation, so results stay deterministic.
+  //   splits == 0 : BALANCED (data-parallel + stream-K, see bal_plan): all but the last full round run whole tiles;
+  //                 the units of the remaining tiles are dealt out to all CTAs in equal contiguous ranges of U
+  //                 units, so the SMs finish together however many tiles the (device-side) row count yields, and
+  //                 only tiles cut by a range boundary pay for partial sums.
+  // Segments that do not cover a whole tile write raw partial sums to the workspace; tc_reduce_kernel sums a tile's
+  // segments in a fixed order and applies bias + activation, so results stay deterministic.
   const bool balanced = (splits == 0);
-  const long long total_units = tiles * nchunks;
-  const long long U = balanced ? max((total_units + gridDim.x - 1) / gridDim.x, static_cast<long long>((nchunks + 2) / 3)) : 0;
+  const BalPlan plan = bal_plan(tiles, gridDim.x, nchunks);
+  const long long rem_tile0 = balanced ? plan.rem_tile0 : 0;            // first stream-K tile
+  const long long rem_units = balanced ? (tiles - rem_tile0) * nchunks : 0;
+  const long long U = plan.U;
   long long u = balanced ? static_cast<long long>(blockIdx.x) * U : 0;
-  const long long u_end = balanced ? min(total_units, u + U) : 0;
+  const long long u_end = balanced ? min(rem_units, u + U) : 0;
   long long item = blockIdx.x;
-  const long long items = balanced ? 0 : tiles * splits;
+  const long long items = balanced ? rem_tile0 : tiles * splits;
   while (true) {
     long long tile;
     int cb, ce, slab;
     bool whole;
-    if (balanced) {
+    long long rem_t = 0;                                                // remainder-tile index (balanced partials)
+    if (balanced && item < items) {                                     // data-parallel rounds
+      tile = item;
+      cb = 0; ce = nchunks; slab = 0; whole = true;
+      item += gridDim.x;
+    } else if (balanced) {                                              // stream-K over the remainder tiles
       if (u >= u_end) break;
-      tile = u / nchunks;
-      cb = static_cast<int>(u - tile * nchunks);
+      rem_t = u / nchunks;
+      tile = rem_tile0 + rem_t;
+      cb = static_cast<int>(u - rem_t * nchunks);
       ce = static_cast<int>(min(static_cast<long long>(nchunks), cb + (u_end - u)));
-      slab = static_cast<int>(blockIdx.x - (tile * nchunks) / U);
+      slab = static_cast<int>(blockIdx.x - (rem_t * nchunks) / U);
       whole = (cb == 0 && ce == nchunks);
       u += ce - cb;
     } else {
@@ -569,11 +602,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       const int m = m0 + my_row;
       if (m < rows && !whole) {
         // raw partial sums of this segment (bias / activation are applied by the reduce pass)
-        float* pr = partial + (static_cast<long long>(slab) * d.max_rows + m) * d.ldy;
+        if (balanced) {                                // compact workspace: [remainder tile][slab][256 rows][BN]
+          float* pr = partial + ((rem_t * plan.slabs + slab) * TC_BM + my_row) * BN + my_ch * ACC;
 #pragma unroll
-        for (int j = 0; j < ACC; j += 4) {
-          const int co = n0 + my_ch * ACC + j;       // ldy % 4 == 0: a quad that starts below cout stays inside the row
-          if (co < d.cout) *reinterpret_cast<float4*>(pr + co) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          for (int j = 0; j < ACC; j += 4) *reinterpret_cast<float4*>(pr + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {                                       // split-K: [slab][max_rows][ldy]
+          float* pr = partial + (static_cast<long long>(slab) * d.max_rows + m) * d.ldy;
+#pragma unroll
+          for (int j = 0; j < ACC; j += 4) {
+            const int co = n0 + my_ch * ACC + j;     // ldy % 4 == 0: a quad that starts below cout stays inside the row
+            if (co < d.cout) *reinterpret_cast<float4*>(pr + co) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          }
         }
       } else if (m < rows) {
         float* yr = d.y + static_cast<long long>(m) * d.ldy;
@@ -649,9 +688,10 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
   }
 }
 
-// y[m, co] = act(bias[co] + sum_s partial[s][m][co]) in a fixed order (deterministic).  splits >= 2: every tile has
-// `splits` slabs.  splits == 0 (balanced): the number of slabs of a tile follows from the same unit arithmetic the
-// conv kernel used (grid = its CTA count); tiles that one CTA covered entirely were already finished there.
+// y[m, co] = act(bias[co] + sum_s partial_s[m][co]) in a fixed order (deterministic).  splits >= 2: every tile has
+// `splits` slabs laid out [slab][max_rows][ldy].  splits == 0 (balanced): only the remainder tiles have partial sums,
+// laid out [remainder tile][slab][256][BN]; the number of segments of a tile follows from the same unit arithmetic the
+// conv kernel used (grid = its CTA count); a remainder tile that one CTA covered entirely was finished there.
 __global__ void tc_reduce_kernel(const float* __restrict__ partial, int splits, int grid, int BN, int nchunks,
                                  const float* __restrict__ bias, float* __restrict__ y, int ldy, int cout,
                                  const int32_t* __restrict__ count, int max_rows, int act, float act_param) {
@@ -659,22 +699,25 @@ __global__ void tc_reduce_kernel(const float* __restrict__ partial, int splits, 
   const long long slab_sz = static_cast<long long>(max_rows) * ldy;
   const int n_tiles = (cout + BN - 1) / BN;
   const long long tiles = static_cast<long long>((rows + TC_BM - 1) / TC_BM) * n_tiles;
-  const long long total_units = tiles * nchunks;
-  const long long U = splits == 0 ? max((total_units + grid - 1) / grid, static_cast<long long>((nchunks + 2) / 3)) : 0;
+  const BalPlan plan = bal_plan(tiles, grid, nchunks);
+  const long long rem_tile0 = splits == 0 ? plan.rem_tile0 : 0;
+  const long long U = plan.U;
   const int quads = BN >> 2;                         // float4 columns of a tile (ldy is a multiple of 4)
   // one CTA per tile per round: the slab arithmetic is per tile, the element loop has no divisions by run-time values
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (long long tile = rem_tile0 + blockIdx.x; tile < tiles; tile += gridDim.x) {
     int nslabs = splits;
+    const long long rem_t = tile - rem_tile0;
     if (splits == 0) {
-      const long long first = (tile * nchunks) / U, last = ((tile + 1) * nchunks - 1) / U;
+      const long long first = (rem_t * nchunks) / U, last = ((rem_t + 1) * nchunks - 1) / U;
       if (first == last) continue;                   // whole tile: already written with bias + activation
       nslabs = static_cast<int>(last - first + 1);
     }
     const int m0 = static_cast<int>(tile / n_tiles) * TC_BM;
     const int co0 = static_cast<int>(tile % n_tiles) * BN;
     const int mrows = min(TC_BM, rows - m0);
+    const float* pbal = partial + rem_t * plan.slabs * TC_BM * BN;
     for (int e = threadIdx.x; e < mrows * quads; e += blockDim.x) {
-      const int r = e / quads, q = e - r * quads;    // quads is a power of two times {8,16,32}: cheap 32-bit division
+      const int r = e / quads, q = e - r * quads;
       const int co = co0 + (q << 2);
       if (co >= cout) continue;
       const long long o = static_cast<long long>(m0 + r) * ldy + co;
@@ -686,7 +729,8 @@ __global__ void tc_reduce_kernel(const float* __restrict__ partial, int splits, 
         if (co + 3 < cout) v.w = __ldg(bias + co + 3);
       }
       for (int sidx = 0; sidx < nslabs; ++sidx) {
-        const float4 p = __ldg(reinterpret_cast<const float4*>(partial + sidx * slab_sz + o));
+        const float4 p = splits == 0 ? __ldg(reinterpret_cast<const float4*>(pbal + (static_cast<long long>(sidx) * TC_BM + r) * BN + (q << 2)))
+                                     : __ldg(reinterpret_cast<const float4*>(partial + sidx * slab_sz + o));
         v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
       }
       v.x = activate(v.x, act, act_param); v.y = activate(v.y, act, act_param);
@@ -759,7 +803,9 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   if (rc != WMD_OK || splits == 1) return rc;
   const int nchunks = d.taps * ((d.c0 + TC_BK - 1) / TC_BK + (d.c1 + TC_BK - 1) / TC_BK);
   const long long all_tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN);
-  tc_reduce_kernel<<<static_cast<int>(all_tiles < 8 * cap ? all_tiles : 8 * cap), 256, 0, stream>>>(partial, splits, grid, BN, nchunks, d.bias, d.y, d.ldy, d.cout,
+  // balanced: only the stream-K tiles (fewer than two rounds) can have partial sums
+  const long long red_grid = splits == 0 ? (all_tiles < 2 * cap ? all_tiles : 2 * cap) : (all_tiles < 8 * cap ? all_tiles : 8 * cap);
+  tc_reduce_kernel<<<static_cast<int>(red_grid < 1 ? 1 : red_grid), 256, 0, stream>>>(partial, splits, grid, BN, nchunks, d.bias, d.y, d.ldy, d.cout,
                                                               d.count, d.max_rows, d.act, d.act_param);
   return launched();
 }
@@ -794,8 +840,9 @@ extern "C" int wmd_pack_conv_weight_tc_f32(const float* w, float* packed, int Co
 
 extern "C" size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits) {
   if (splits == 1) return 0;
-  const size_t slabs = splits == 0 ? 4 : static_cast<size_t>(splits);      // balanced mode: <= 4 segments per tile
-  return slabs * static_cast<size_t>(max_rows) * static_cast<size_t>(ldy) * sizeof(float);
+  if (splits == 0)   // balanced: [stream-K tile][slab][256 rows][N <= 128] floats, tiles x slabs <= CTAs x kBalSlabs whatever the layer size
+    return static_cast<size_t>(wmd::sm_count()) * wmd::kBalSlabs * wmd::TC_BM * 128 * sizeof(float);
+  return static_cast<size_t>(splits) * static_cast<size_t>(max_rows) * static_cast<size_t>(ldy) * sizeof(float);
 }
 
 extern "C" int wmd_conv_rows_tc_f32(const wmd_conv_desc* dp, wmd_stream_t stream) {

@@ -280,34 +280,21 @@ def scatter_rows(rows, c, pixels, count, n, h, w, max_rows=None, out=None):
     return out
 
 
-_sm_count = {}
-
-
-TC_BALANCE_WS_LIMIT = 2 << 30      # bytes of partial-sum workspace we are willing to hold for balanced scheduling
-
-
 def tc_splits(max_rows, cout, nchunks, device, ldy=None):
-    """Scheduling mode of the tcgen05 engine for one launch: 1 = whole tiles, 0 = balanced (stream-K style).
+    """Scheduling mode of the tcgen05 engine for one launch: 1 = whole tiles, 0 = balanced (data-parallel + stream-K).
 
     One CTA per SM runs equal (256-row x N-channel) tiles, so with few tiles per SM the last round is mostly idle
-    (320 tiles on 148 SMs = 72 %) and a layer with fewer tiles than SMs leaves SMs dark.  Balanced mode deals the
-    (tile, chunk) units out evenly on the device and finishes cut tiles with a fixed-order reduce pass; it costs one
-    extra write + read of the cut tiles' outputs, which only pays for long reductions.  Measured on B200 (R50 1024x320,
-    scripts/conv_layers_bench.py): bs32 upconv(4,0) 0.85 -> 0.55 ms, upconv(4,1) 1.62 -> 1.36, upconv(3,1) 0.87 -> 0.71,
-    upconv(2,1) 0.75 -> 0.69; the 1x1 head stages (1-8 chunks) and the short 3x3 reductions (<= 72 chunks) lose 5-25 %
-    at bs32 but win when the launch cannot fill the SMs (bs4 upconv(3,0) 0.133 -> 0.098).
-    Needs a workspace of 4 x max_rows x ldy floats."""
-    lib = _lib.load()
-    ldy = pad4(cout) if ldy is None else ldy
-    if 16 * max_rows * ldy > TC_BALANCE_WS_LIMIT:
-        return 1
-    if nchunks >= 80:
-        return 0
-    key = str(device)
-    if key not in _sm_count:
-        _sm_count[key] = torch.cuda.get_device_properties(device).multi_processor_count
-    tiles = -(-max_rows // 256) * -(-cout // lib.wmd_conv_tc_tile_n(cout))
-    return 0 if (nchunks >= 32 and tiles <= 0.75 * _sm_count[key]) else 1
+    (320 tiles on 148 SMs = 72 %; the sparse levels' tile count is only known on the device) and a layer with fewer
+    tiles than SMs leaves SMs dark.  Balanced mode runs the full rounds as whole tiles and deals the (tile, chunk)
+    units of the remainder tiles out evenly on the device; only those tiles go through the fixed-order reduce pass
+    (workspace: CTAs x 8 x 256 x 128 floats).  The extra pass only pays for long reductions - measured on B200
+    (scripts/conv_layers_bench.py, R50 1024x320): bs32 upconv(4,0) 0.67 -> 0.45 ms, upconv(4,1) 1.27 -> 1.02,
+    upconv(3,1) 0.69 -> 0.60, upconv(2,1) 0.61 -> 0.57; reductions of <= 72 chunks (and the 1x1 head stages) lose
+    10-20 % at every batch size."""
+    return 0 if nchunks >= TC_BALANCE_MIN_CHUNKS else 1
+
+
+TC_BALANCE_MIN_CHUNKS = 80
 
 
 class PackedW:
