@@ -64,15 +64,17 @@ def synth_features(wl, n, first_sample, pin):
 
 
 def measured_peaks():
-    """(HBM GB/s, bf16 dense TFLOP/s burst, source)."""
+    """(HBM GB/s, bf16 dense TFLOP/s burst, source, bf16 dense TFLOP/s sustained or None)."""
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
             d = json.load(open(path))
-            return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+            sus = d.get("bf16_tflops_sustained")
+            return (float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)",
+                    float(sus) if sus else None)
         except Exception:
             pass
-    return 6650.0, 1590.0, "fallback (B200_PROFILING.md 6.65 TB/s, 1.59 PFLOP/s)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md 6.65 TB/s, 1.59 PFLOP/s)", None
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -174,11 +176,38 @@ def account(name, info):
     if name == "gate_map":
         return 9 * info["count"], 0
     if name in ("nchw_to_rows", "rows_to_nchw"):
-        return 8 * info["n"] * info["c"] * info["hw"], 0
+        px = _as_int(info.get("marked"), info["n"] * info["hw"])      # gated move: only the marked pixels' rows
+        return 8 * info["c"] * px + (info["n"] * info["hw"] if info.get("marked") is not None else 0), 0
     return 0, 0
 
 
-def roofline_from(records, peak_gbs, peak_tf, peak_src, steps):
+def conv_layer_table(records, peak_gbs, peak_tf, steps):
+    """One line per gather-GEMM launch of a step (mean over the profiled steps): shape, active rows, time, rates."""
+    convs = [(name, ms, info) for name, ms, info in records if name in ("conv_rows", "conv_rows_tc")]
+    per_step = len(convs) // max(steps, 1)
+    if per_step == 0 or per_step * steps != len(convs):
+        return []
+    table = []
+    for k in range(per_step):
+        same = convs[k::per_step]
+        name, _, info = same[0]
+        ms = sum(m for _, m, _ in same) / len(same)
+        by, fl = account(name, info)
+        rows = min(_as_int(info["count"], info["n"] * info["h"] * info["w"]), info["max_rows"])
+        tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        line = {"engine": "tcgen05_3xtf32" if name == "conv_rows_tc" else "fp32_fma", "taps": info["taps"],
+                "cin": [info["c0"], info["c1"]], "cout": info["cout"], "grid": [info["n"], info["h"], info["w"]],
+                "rows": rows, "us": round(1e3 * ms, 1), "fp32_eq_tflops": round(tf, 1),
+                "hbm_frac": round(by / (ms * 1e-3) / 1e9 / peak_gbs, 3) if ms > 0 else 0.0}
+        if name == "conv_rows_tc":
+            line["tensor_frac"] = round(3.0 * tf / (peak_tf / 2.0), 3)
+        else:
+            line["fma_frac"] = round(tf / FP32_SIMT_PEAK_TFLOPS, 3)
+        table.append(line)
+    return table
+
+
+def roofline_from(records, peak_gbs, peak_tf, peak_src, steps, peak_tf_sustained=None):
     agg = {}
     for name, ms, info in records:
         by, fl = account(name, info)
@@ -208,7 +237,9 @@ def roofline_from(records, peak_gbs, peak_tf, peak_src, steps):
                 "launches_per_step": hbm_view["launches_per_step"], "share_of_kernel_time": hbm_view["share_of_kernel_time"],
                 "bytes_per_launch": hbm_view["bytes_per_launch"],
                 "hbm_view": {"achieved_gbs": hbm_view["achieved"], "peak_gbs": peak_gbs, "frac": hbm_view["frac"]},
-                "peak_source": peak_src + ": bf16_tflops / 2 for tf32",
+                "frac_of_sustained_peak": round(executed / (peak_tf_sustained / 2.0), 4) if peak_tf_sustained else None,
+                "peak_source": peak_src + ": burst bf16_tflops / 2 for tf32 (each launch is timed alone between two "
+                               "events; frac_of_sustained_peak uses bf16_tflops_sustained / 2)",
                 "note": "tcgen05.mma.kind::tf32, 3 MMAs per fp32 product (hi*hi + hi*lo + lo*hi), fp32 accumulation in "
                         "TMEM; A gathered by TMA gather4 and moved to TMEM by split warps; the N=128 layers run at "
                         "~0.8 of this peak, the N<=64 layers are bound by the gather (L2->SM path), see DESIGN.md 4"}
@@ -223,6 +254,19 @@ def roofline_from(records, peak_gbs, peak_tf, peak_src, steps):
             main["traffic"] = json.load(open(traffic_file)).get(dom)
         except Exception:
             pass
+    # whole step against the HBM roof (north_star: "fraction of the HBM roofline" for the fused decoder): the summed
+    # algorithmic bytes of every launch of a step over the summed kernel time
+    step_bytes = sum(a["bytes"] for a in agg.values()) / max(steps, 1)
+    step_flops = sum(a["flops"] for a in agg.values()) / max(steps, 1)
+    step_ms = total_ms / max(steps, 1)
+    main["step_view"] = {"algorithmic_bytes_per_step": int(step_bytes), "kernel_ms_per_step": round(step_ms, 3),
+                         "hbm_gbs": round(step_bytes / (step_ms * 1e-3) / 1e9, 1),
+                         "hbm_frac": round(step_bytes / (step_ms * 1e-3) / 1e9 / peak_gbs, 4),
+                         "fp32_eq_tflops": round(step_flops / (step_ms * 1e-3) / 1e12, 1),
+                         "hbm_floor_ms": round(step_bytes / (peak_gbs * 1e9) * 1e3, 3),
+                         "tf32x3_floor_ms": round(3.0 * step_flops / (peak_tf / 2.0 * 1e12) * 1e3, 3),
+                         "note": "the decoder is tensor-bound, not HBM-bound, at fp32-faithful precision: 3 tf32 MMAs per "
+                                 "product put the tensor-pipe floor above the HBM floor (both listed)"}
     return main, out
 
 
@@ -245,9 +289,13 @@ def _cpu_setup(wl_name):
     return wl, _CPU_PARAMS[wl_name]
 
 
-def _cpu_frame(wl, sd, f):
+def _cpu_frame(wl, sd, f, batch=None):
     from oracle import kitti as okitti                     # allowed here: cpu_baseline / --impl reference legs only
-    feats = synth_features(wl, 1, f % wl["per_gpu_batch"], pin=False)
+    b = f % wl["per_gpu_batch"]
+    if batch is not None:                                  # frame b of the step's own (host) feature batch
+        feats = [t[b:b + 1].contiguous() for t in batch]
+    else:
+        feats = synth_features(wl, 1, b, pin=False)
     t0 = time.perf_counter()
     with torch.no_grad():
         okitti.sparse_forward(sd, feats, THRESH)
@@ -278,14 +326,15 @@ def cpu_pick_threads(wl_name):
     return best
 
 
-def cpu_frames_per_sec(wl_name, frames, budget_s=20.0, first_frame=0):
+def cpu_frames_per_sec(wl_name, frames, budget_s=20.0, first_frame=0, batch=None):
     """Times oracle.kitti.sparse_forward (the reference's batch-1 sparse path, restated) on the host cores:
-    up to `frames` frames, stopping early once `budget_s` seconds of CPU work are spent."""
+    up to `frames` frames, stopping early once `budget_s` seconds of CPU work are spent.  `batch`: host feature
+    tensors to take the frames from (the GPU arm's own step inputs); otherwise frames are generated one by one."""
     wl, sd = _cpu_setup(wl_name)
     torch.set_num_threads(cpu_pick_threads(wl_name))
     times = []
     for f in range(frames):
-        times.append(_cpu_frame(wl, sd, first_frame + f))
+        times.append(_cpu_frame(wl, sd, first_frame + f, batch))
         if sum(times) >= budget_s:
             break
     return len(times) / sum(times), times
@@ -356,7 +405,7 @@ def run_native(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    peak_gbs, peak_tf, peak_src = measured_peaks()
+    peak_gbs, peak_tf, peak_src, peak_tf_sus = measured_peaks()
 
     def setup(wl_name):
         wl = WORKLOADS[wl_name]
@@ -431,39 +480,73 @@ def run_native(args, rank, world, local_rank):
     torch.cuda.empty_cache()
 
     # ---- 2. end to end: host features -> H2D (copy stream, double buffered) -> decode -> D2H of disp0
+    # zero_copy = indices of skip maps that stay in pinned host memory and are read in place by the gated layout move
+    # (only the rows under the level's upsample mask cross PCIe); the others are DMA-copied one step ahead.
     copy_stream = torch.cuda.Stream()
-    bufs = [[torch.empty_like(f, device=dev) for f in host] for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
     disp_host = torch.empty((n_local, 1, wl["height"], wl["width"]), dtype=torch.float32).pin_memory()
-    h2d_bytes = sum(f.numel() * 4 for f in host)
     d2h_bytes = disp_host.numel() * 4 + 9 * (n_local + 1) * 4
-    state = {"i": 0}
-    graphs_e2e = [graphs.GraphedSparseDecoder(dec, b, THRESH) for b in bufs] if use_graph else None
 
-    def enqueue_copy(slot):
-        with torch.cuda.stream(copy_stream):
-            for dst, src in zip(bufs[slot], host):
-                dst.copy_(src, non_blocking=True)
-            ready[slot].record(copy_stream)
+    def run_e2e(zero_copy):
+        dma = [k for k in range(len(host)) if k not in zero_copy]
+        bufs = [[host[k] if k in zero_copy else torch.empty_like(host[k], device=dev) for k in range(len(host))]
+                for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {"i": 0}
+        graphs_e2e = [graphs.GraphedSparseDecoder(dec, b, THRESH) for b in bufs] if use_graph else None
 
-    def e2e_step():
-        i = state["i"]
-        slot = i % 2
-        enqueue_copy(1 - slot)                                   # next step's inputs overlap this step's compute
-        torch.cuda.current_stream().wait_event(ready[slot])
-        o = graphs_e2e[slot].replay() if use_graph else dec(bufs[slot], THRESH)   # ends with the count read-back (host sync)
-        if world > 1:
-            shard.all_gather_batch(o[("disp", 0)], n_global)
-        disp_host.copy_(o[("disp", 0)], non_blocking=True)
-        copy_stream.wait_stream(torch.cuda.current_stream())     # slot is free for the copy after next
-        state["i"] = i + 1
+        def enqueue_copy(slot):
+            with torch.cuda.stream(copy_stream):
+                for k in dma:
+                    bufs[slot][k].copy_(host[k], non_blocking=True)
+                ready[slot].record(copy_stream)
 
-    enqueue_copy(0)
-    e2e_ms = time_device(e2e_step, args.steps, 2, dist, world)
+        def e2e_step():
+            i = state["i"]
+            slot = i % 2
+            enqueue_copy(1 - slot)                                   # next step's inputs overlap this step's compute
+            torch.cuda.current_stream().wait_event(ready[slot])
+            o = graphs_e2e[slot].replay() if use_graph else dec(bufs[slot], THRESH)   # ends with the count read-back (host sync)
+            if world > 1:
+                shard.all_gather_batch(o[("disp", 0)], n_global)
+            disp_host.copy_(o[("disp", 0)], non_blocking=True)
+            copy_stream.wait_stream(torch.cuda.current_stream())     # slot is free for the copy after next
+            state["i"] = i + 1
+            last["e2e_out"] = o
+
+        enqueue_copy(0)
+        ms_ = time_device(e2e_step, args.steps, 2, dist, world)
+        o = last.pop("e2e_out")
+        h2d = sum(host[k].numel() * 4 for k in dma)
+        in_place = 0
+        for k in zero_copy:                                          # 128-byte requests the gated move issued to the host
+            up = o[("upsample_mask", k)].reshape(n_local, -1)
+            groups = int(up.reshape(n_local, -1, 32).any(-1).sum().item()) if up.shape[1] % 32 == 0 else up.numel() // 32
+            in_place += groups * 128 * host[k].shape[1]
+        del graphs_e2e, bufs
+        torch.cuda.empty_cache()
+        return ms_, h2d, in_place
+
+    h2d_bytes = sum(f.numel() * 4 for f in host)
+    e2e_ms, e2e_h2d, _ = run_e2e(())
+    e2e_note = "pinned host features; H2D double-buffered on a copy stream; PCIe-bound"
+    e2e_dma = None
+    if dec.gated_layout and args.e2e_zero_copy:
+        zc = tuple(int(k) for k in args.e2e_zero_copy.split(","))
+        zc_ms, zc_h2d, zc_in_place = run_e2e(zc)
+        log("[e2e] DMA %.2f ms/step (%.0f MB) ; zero-copy skips %s %.2f ms/step (%.0f MB DMA + %.0f MB in place)"
+            % (e2e_ms / args.steps, e2e_h2d / 1e6, zc, zc_ms / args.steps, zc_h2d / 1e6, zc_in_place / 1e6))
+        if zc_ms < e2e_ms:
+            e2e_dma = {"value": round(n_global * args.steps / (e2e_ms * 1e-3), 1), "unit": UNIT,
+                       "h2d_bytes_per_step": e2e_h2d, "ms_per_step": round(e2e_ms / args.steps, 3),
+                       "note": "every feature map DMA-copied whole (the plain path)"}
+            e2e_ms, e2e_h2d = zc_ms, zc_h2d + zc_in_place
+            e2e_note = ("pinned host features; feats[4..%d] DMA-copied one step ahead on a copy stream, skip maps %s read "
+                        "in place from pinned host memory by the gated layout move (only 32-pixel groups under the "
+                        "level's upsample mask cross PCIe: %.0f MB of %.0f MB); h2d_bytes_per_step = DMA bytes + those "
+                        "in-place reads" % (max(zc) + 1, list(zc), zc_in_place / 1e6,
+                                            sum(host[k].numel() * 4 for k in zc) / 1e6))
     e2e_value = n_global * args.steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if sampler else None
-    del graphs_e2e, bufs
-    torch.cuda.empty_cache()
 
     # ---- 3. per-kernel roofline pass (same workload, CUDA events around every libwmd launch)
     prof_steps = 3
@@ -474,7 +557,9 @@ def run_native(args, rank, world, local_rank):
         dec(resident, THRESH)
     torch.cuda.synchronize()
     ops.set_profiler(None)
-    roof, roof_all = roofline_from(prof.results(), peak_gbs, peak_tf, peak_src, prof_steps)
+    prof_records = prof.results()
+    roof, roof_all = roofline_from(prof_records, peak_gbs, peak_tf, peak_src, prof_steps, peak_tf_sus)
+    conv_layers = conv_layer_table(prof_records, peak_gbs, peak_tf, prof_steps)
 
     # ---- 4. secondary workload of the metric (device-resident only)
     also = None
@@ -503,11 +588,11 @@ def run_native(args, rank, world, local_rank):
     # ---- 5. CPU baseline (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        fps, times = cpu_frames_per_sec(args.workload, args.cpu_frames, budget_s=20.0)
+        fps, times = cpu_frames_per_sec(args.workload, args.cpu_frames, budget_s=20.0, batch=host)
         cpu = {"value": round(fps, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "%d frames of %s (seeds of frames 0..%d), one at a time as the reference requires; %.1fs of "
-                         "CPU work; intra-op threads chosen by probe out of %d usable cores"
-                         % (len(times), args.workload, len(times) - 1, sum(times), _affinity_cores())}
+               "sample": "%d frames of %s (the GPU arm's own %d-frame step, cycled), one at a time as the reference "
+                         "requires; %.1fs of CPU work; intra-op threads chosen by probe out of %d usable cores"
+                         % (len(times), args.workload, n_local, sum(times), _affinity_cores())}
 
     launches_t = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
@@ -530,18 +615,22 @@ def run_native(args, rank, world, local_rank):
                 "timed_region": "decoder forward on NCHW fp32 features resident in HBM, incl. layout transposes, "
                                 "mask/compaction, the total_ops count read-back and (N>1) the all-gather",
                 "launch_mode": "CUDA graph replay (graphs.GraphedSparseDecoder)" if use_graph else "eager",
+                "layout_moves": "%s, %s" % ("gated by the upsample mask" if dec.gated_layout else "whole maps",
+                                            "side stream" if dec.overlap_layout else "in order"),
             },
             "value_eager": {"value": round(value_eager, 1), "unit": UNIT, "ms_per_step": round(ms_eager / args.steps, 3),
                             "note": "same step issued launch by launch from Python (no CUDA graph)"},
             "value_channels_last": {"value": round(value_cl, 1), "unit": UNIT, "ms_per_step": round(ms_cl / args.steps, 3),
                                     "note": "same step, encoder features in torch.channels_last: used zero-copy, no layout transposes"},
-            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(e2e_ms / args.steps, 3),
-                    "note": "pinned host features; H2D double-buffered on a copy stream; PCIe-bound"},
+                    "note": e2e_note},
+            "e2e_dma": e2e_dma,
             "gpu_launches": int(launches_t.item()),
             "clocks": clocks,
             "roofline": roof,
             "roofline_kernels": roof_all,
+            "conv_layers": conv_layers,
             "cpu_baseline": cpu,
             "also": also,
         }
@@ -558,8 +647,11 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=MAIN, choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-frames", type=int, default=48)
+    ap.add_argument("--cpu-frames", type=int, default=400)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-zero-copy", default=os.environ.get("WMD_E2E_ZERO_COPY", ""),
+                    help="comma list of skip-map indices (e.g. 0,1) the e2e pass leaves in pinned host memory; needs "
+                         "the gated layout move (WMD_GATED_LAYOUT=1)")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

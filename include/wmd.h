@@ -121,6 +121,12 @@ int wmd_gate_map(const uint8_t* gate, const int32_t* idxmap, int32_t* out, long 
  * wire format (layers.py:358) at the functional API. */
 int wmd_nchw_to_rows_f32(const float* src, float* dst, int N, int C, long long HW, int ld, wmd_stream_t stream);
 int wmd_rows_to_nchw_f32(const float* src, float* dst, int N, int C, long long HW, int ld, wmd_stream_t stream);
+/* Same move, but only for the pixels marked in gate (N, HW) bytes: rows of unmarked pixels are left untouched and
+ * their source is not read (whole 32-pixel groups without a mark cost no traffic).  The sparse levels read a skip map
+ * only under the level's upsample mask (sparse_upsample: skip[mask], KITTI/layers.py:500; the conv's gate argument
+ * below), so the decoder passes that mask here and the transpose scales with the mask density. */
+int wmd_nchw_to_rows_gated_f32(const float* src, float* dst, const uint8_t* gate, int N, int C, long long HW, int ld,
+                               wmd_stream_t stream);
 /* rows at an active-pixel list <-> dense NCHW (x[mask] selection, depth_decoder.py:347; make_result, layers.py:365-368) */
 int wmd_gather_rows_nchw_f32(const float* src_nchw, float* rows, int ld, int C, const int32_t* pixels,
                              const int32_t* count, int max_rows, int N, int H, int W, wmd_stream_t stream);

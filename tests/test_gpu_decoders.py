@@ -315,3 +315,52 @@ def test_cuda_graph_replay_matches_eager_and_follows_input_updates():
         else:
             assert out[k] == v, key_str(k)
     assert not torch.equal(ref[("disp", 0)], eager[("disp", 0)])
+
+
+def test_layout_move_options_are_bit_identical_eager_and_graphed():
+    """overlap_layout: the skip maps' NCHW->rows transposes run on a side stream (fork after the current stream,
+    join by event before first use).  gated_layout: a sparse level's skip map is transposed only under its upsample
+    mask (the only rows upconv(i,1) reads).  Neither changes what is computed: every output must equal the plain
+    in-order run bit for bit, launch by launch and inside a captured CUDA graph."""
+    from wavelet_monodepth_b200 import graphs
+    mod, _, feats = _full_kitti(synth.RESNET18_CH, 3, 192, 640)
+    mod.overlap_layout = mod.gated_layout = False
+    want = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in mod(feats, 0.05).items()}
+    dens = float(want[("upsample_mask", 0)].float().mean())
+    assert 0.0 < dens < 0.9, dens                            # the gate really removes rows at the finest level
+    try:
+        for overlap, gated in ((True, False), (False, True), (True, True)):
+            mod.overlap_layout, mod.gated_layout = overlap, gated
+            for _ in range(3):                               # repeated: allocator reuse across the two streams
+                got = mod(feats, 0.05)
+                torch.cuda.synchronize()
+                for k, v in want.items():
+                    assert (torch.equal(got[k], v) if torch.is_tensor(v) else got[k] == v), (overlap, gated, key_str(k))
+            g = graphs.GraphedSparseDecoder(mod, feats, 0.05)
+            for _ in range(2):
+                got = g.replay()
+                for k, v in want.items():
+                    assert (torch.equal(got[k], v) if torch.is_tensor(v) else got[k] == v), (overlap, gated, key_str(k))
+            del g
+        # gated move reading the two finest skip maps in place from pinned host memory (zero-copy over PCIe)
+        on_host = [feats[0].cpu().pin_memory(), feats[1].cpu().pin_memory()] + list(feats[2:])
+        for overlap in (False, True):
+            mod.overlap_layout, mod.gated_layout = overlap, True
+            got = mod(on_host, 0.05)
+            torch.cuda.synchronize()
+            for k, v in want.items():
+                assert (torch.equal(got[k], v) if torch.is_tensor(v) else got[k] == v), ("host", overlap, key_str(k))
+        g = graphs.GraphedSparseDecoder(mod, on_host, 0.05)
+        got = g.replay()
+        for k, v in want.items():
+            assert (torch.equal(got[k], v) if torch.is_tensor(v) else got[k] == v), ("host graph", key_str(k))
+        del g
+        with pytest.raises(kd.WmdError):                       # pageable host memory is refused
+            mod([feats[0].cpu()] + list(feats[1:]), 0.05)
+        with pytest.raises(kd.WmdError):                       # a dense level's skip map must be on the device
+            mod(list(feats[:3]) + [feats[3].cpu().pin_memory(), feats[4]], 0.05)
+        mod.gated_layout = False
+        with pytest.raises(kd.WmdError):                       # without the gated move nothing reads host memory
+            mod(on_host, 0.05)
+    finally:
+        mod.overlap_layout = mod.gated_layout = False

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from oracle import haar as ohaar
 from oracle import kitti as okitti
 from oracle import sparse_ops as osp
-from wavelet_monodepth_b200 import ops, wavelets
+from wavelet_monodepth_b200 import _lib, ops, wavelets
 from wavelet_monodepth_b200._lib import (ACT_ELU, ACT_LRELU, ACT_NONE, ACT_SIGMOID, PAD_REFLECT, PAD_REPLICATE,
                                          PAD_ZERO)
 
@@ -362,3 +362,24 @@ def test_fused_idwt_bilinear_vs_torch(h, w, size, ac):
     got = ops.idwt_bilinear(ll.to(DEV), hf.to(DEV), size, disp_scale=0.25, clamp01=True, align_corners=ac)
     assert got.shape == want.shape
     assert float((got.cpu() - want).abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("n,c,h,w,p", [(2, 64, 12, 40, 0.3), (1, 5, 7, 9, 0.5), (3, 96, 16, 128, 0.02), (2, 32, 8, 64, 0.0),
+                                       (1, 130, 5, 131, 1.0)])
+def test_gated_layout_move_writes_exactly_the_marked_rows(n, c, h, w, p):
+    """wmd_nchw_to_rows_gated_f32: marked pixels get the same row the plain transpose writes (bit-exact),
+    unmarked rows keep whatever the buffer held."""
+    g = torch.Generator().manual_seed(n * 1000 + c)
+    x = torch.randn(n, c, h, w, generator=g).to(DEV)
+    gate = (torch.rand(n, 1, h, w, generator=g) < p).to(torch.uint8).to(DEV)
+    want = ops.nchw_to_rows(x)
+    ld = want.shape[1]
+    lib = _lib.load()
+    rows = torch.full((n * h * w, ld), -7.0, device=DEV)
+    rc = lib.wmd_nchw_to_rows_gated_f32(_lib.ptr(x), _lib.ptr(rows), _lib.ptr(gate), n, c, h * w, ld, _lib.stream_ptr())
+    assert rc == 0
+    on = gate.reshape(-1).bool()
+    assert torch.equal(rows[on], want[on])
+    assert bool((rows[~on] == -7.0).all())
+    got = ops.nchw_to_rows(x, gate=gate)                     # wrapper (fresh buffer): marked rows only are defined
+    assert torch.equal(got[on], want[on])

@@ -69,6 +69,7 @@ SIGNATURES = {
                                  c_void_p]),
     "wmd_gate_map": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "wmd_nchw_to_rows_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
+    "wmd_nchw_to_rows_gated_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "wmd_rows_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "wmd_gather_rows_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                          c_int, c_void_p]),
@@ -130,6 +131,21 @@ def check(rc, what):
 
 def stream_ptr():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def host_ptr(t, dtype=None):
+    """Pointer of a contiguous PINNED host tensor, for the one entry point that may read host memory in place
+    (wmd_nchw_to_rows_gated_f32's src: page-locked memory is mapped into the device's address space under UVA, so a
+    kernel reads it across PCIe at the same address).  Pageable memory is refused."""
+    if t.is_cuda:
+        return ptr(t, dtype)
+    if not t.is_pinned():
+        raise WmdError("host features must be pinned (page-locked) to be read by the device; got pageable memory")
+    if dtype is not None and t.dtype != dtype:
+        raise WmdError("expected dtype %s, got %s" % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise WmdError("expected a contiguous tensor")
+    return t.data_ptr()
 
 
 def ptr(t, dtype=None):

@@ -11,13 +11,32 @@ constexpr int kTT = 32;
 // requests; write side: 8 lanes cover the 32 channels of one pixel as float4 (one full 128-byte
 // line per pixel).  The 129-float row pitch makes the transposed shared-memory reads conflict-free.
 constexpr int kTP = 128;   // pixels per tile
+static_assert(kTP / 32 == 4, "the gated variant ORs four group masks");
+//
+// GATED: `gate` (N, HW) bytes marks the pixels whose rows a later kernel will read (the sparse decoder reads a skip
+// map only under its upsample mask - sparse_upsample, KITTI/layers.py:500).  Reads are skipped per 32-pixel group
+// (one 128-byte request) with no marked pixel, writes per unmarked pixel (one 128-byte line), and a tile with no
+// marked pixel returns after one 128-byte look at the gate; unmarked rows of dst are left untouched.
+template <bool GATED>
 __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                           int C, long long HW, int ld) {
+                                                           const uint8_t* __restrict__ gate, int C, long long HW,
+                                                           int ld) {
   __shared__ float tile[kTT][kTP + 1];
+  __shared__ unsigned marked[kTP / 32];
   const int n = blockIdx.z;
   const long long p0 = static_cast<long long>(blockIdx.x) * kTP;
   const int c0 = blockIdx.y * kTT;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (GATED) {
+    if (warp < kTP / 32) {
+      const long long p = p0 + 32 * warp + lane;
+      const bool on = p < HW && gate[static_cast<long long>(n) * HW + p] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (lane == 0) marked[warp] = m;
+    }
+    __syncthreads();
+    if ((marked[0] | marked[1] | marked[2] | marked[3]) == 0u) return;
+  }
   const float* s = src + static_cast<long long>(n) * C * HW;
   float* d = dst + static_cast<long long>(n) * HW * ld;
 #pragma unroll
@@ -26,6 +45,7 @@ __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restri
     const float* row = s + static_cast<long long>(c) * HW;
 #pragma unroll
     for (int j = 0; j < kTP / 32; ++j) {          // four fully coalesced 128-byte requests per channel row
+      if (GATED && marked[j] == 0u) continue;
       const long long p = p0 + lane + 32 * j;
       tile[r][lane + 32 * j] = (c < C && p < HW) ? __ldg(row + p) : 0.f;
     }
@@ -38,6 +58,7 @@ __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restri
     const int pl = it * 32 + warp * 4 + (lane >> 3);          // pixel within the tile
     const long long p = p0 + pl;
     const int c = c0 + 4 * q;
+    if (GATED && ((marked[pl >> 5] >> (pl & 31)) & 1u) == 0u) continue;
     if (p < HW && c < ld) {
       const float4 o = make_float4(tile[4 * q][pl], tile[4 * q + 1][pl], tile[4 * q + 2][pl], tile[4 * q + 3][pl]);
       float* out = d + p * ld + c;
@@ -174,7 +195,19 @@ extern "C" int wmd_nchw_to_rows_f32(const float* src, float* dst, int N, int C, 
   if (N == 0) return WMD_OK;
   dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
   WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
-  nchw_to_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, HW, ld);
+  nchw_to_rows_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, dst, nullptr, C, HW, ld);
+  return launched();
+}
+
+extern "C" int wmd_nchw_to_rows_gated_f32(const float* src, float* dst, const uint8_t* gate, int N, int C,
+                                          long long HW, int ld, wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(src && dst && gate, WMD_ERR_ARG);
+  WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
+  if (N == 0) return WMD_OK;
+  dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
+  WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
+  nchw_to_rows_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, dst, gate, C, HW, ld);
   return launched();
 }
 

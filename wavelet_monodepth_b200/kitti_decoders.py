@@ -18,6 +18,7 @@ What is different underneath (B200-first):
     host sync is one read of the counts at the end for ``total_ops``;
   * training (grad enabled) uses the differentiable path: cuDNN convs + the native IDWT with its adjoint.
 """
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -51,8 +52,22 @@ def _pm(fn):
     return fn() if ops._profiler is not None else None
 
 
-def _need_cuda(feats):
-    for f in feats:
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One side stream per device for the layout moves (created lazily, reused: CUDA graphs fork/join through it)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def _need_cuda(feats, host_ok=()):
+    """host_ok: indices of feature maps that may instead be pinned host tensors (read in place by the gated move)."""
+    for k, f in enumerate(feats):
+        if not f.is_cuda and k in host_ok and f.is_pinned():
+            continue
         if not f.is_cuda:
             raise WmdError("wavelet_monodepth_b200 decoders run on CUDA tensors only: the native kernels have no "
                            "CPU fallback (got a feature map on %s)" % f.device)
@@ -130,6 +145,10 @@ class _WaveDecoderBase(nn.Module):
         # align_corners=False) for s = 1..3 - what KITTI/trainer.py:338-339 computes from every scale - produced
         # straight from the coefficients by the fused IDWT+bilinear kernel
         self.full_res_size = None
+        # run the skip maps' layout transposes on a side stream (WMD_OVERLAP_LAYOUT=0/1 sets the default)
+        self.overlap_layout = os.environ.get("WMD_OVERLAP_LAYOUT", "0") == "1"
+        # transpose a sparse level's skip map only under its upsample mask (WMD_GATED_LAYOUT=0/1 sets the default)
+        self.gated_layout = os.environ.get("WMD_GATED_LAYOUT", "0") == "1"
 
     # ---- packed parameters ------------------------------------------------------------------
     def _upconv(self, i, j):
@@ -174,12 +193,18 @@ class _WaveDecoderBase(nn.Module):
 
         Returns (outputs, count_tensors) where count_tensors[i] = (off2, off4, off5) device int32 (N+1,)
         for sparse levels (None for dense ones)."""
-        _need_cuda(feats)
+        # with gated_layout the skip map of a sparse level i (feats[i-1]) may live in pinned host memory
+        _need_cuda(feats, host_ok=tuple(i - 1 for i in sparse_levels) if self.gated_layout else ())
         out = {}
         n = feats[-1].shape[0]
         dev = feats[-1].device
-        rows_f = {4: ops.nchw_to_rows(feats[4])}
-        x_rows, x_c, prev_map = rows_f[4], feats[4].shape[1], None
+        x_rows, x_c, prev_map = ops.nchw_to_rows(feats[4]), feats[4].shape[1], None
+        # layout moves of the skip maps (NCHW -> pixel-major rows), two options on top of the plain in-order transpose:
+        #  gated_layout   a sparse level reads its skip map only under the upsample mask S3 (sparse_upsample:
+        #                 skip[mask], layers.py:500), so only those rows are produced - the move scales with density;
+        #  overlap_layout the move runs on a side stream next to the level's upconv(i,0), which does not need it
+        #                 (HBM-bound transposes fill the tails of the tensor-bound convolution), joined by an event.
+        side = _side_stream(dev) if self.overlap_layout else None
         h, w = feats[4].shape[2:]
         yl = yh = None
         counts = {}
@@ -190,7 +215,6 @@ class _WaveDecoderBase(nn.Module):
             cs = skip.shape[1]
             if tuple(skip.shape[2:]) != (2 * h, 2 * w):
                 raise WmdError("skip feature %d has shape %s, expected spatial %s" % (i - 1, tuple(skip.shape), (2 * h, 2 * w)))
-            skip_rows = ops.nchw_to_rows(skip)
             masks = None
             if with_masks:
                 if i == 4:
@@ -198,6 +222,13 @@ class _WaveDecoderBase(nn.Module):
                 else:
                     thresh = ops.range_thresh(yl, thresh_ratio)
                     masks = ops.level_masks(yh, thresh)
+            skip_gate = masks["S3"] if (sparse and self.gated_layout) else None
+            skip_done = None
+            if side is not None:
+                skip_rows, skip_done = ops.nchw_to_rows(skip, stream=side, gate=skip_gate)
+            else:
+                skip_rows = ops.nchw_to_rows(skip, gate=skip_gate)
+            if with_masks:
                 for name, key in (("lowres_mask", "S1"), ("upconv0_mask", "S2"), ("upsample_mask", "S3"),
                                   ("upconv1_mask", "S4"), ("wavelet_mask", "S5")):
                     out[(name, i - 1)] = masks[key].view(torch.bool)
@@ -214,6 +245,8 @@ class _WaveDecoderBase(nn.Module):
                 counts[i] = (off2, off4, off5)
                 xa = ops.conv_rows(x_rows, x_c, wp0, b0, c, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, map0=gmap,
                                    pixels=pix2, count=off2[n:], m_in0=_pm(lambda: (gmap >= 0).sum()))
+                if skip_done is not None:
+                    torch.cuda.current_stream(dev).wait_event(skip_done)
                 xb = ops.conv_rows(xa, c, wp1, b1, c, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_ELU, map0=map2,
                                    shift0=1, x1=skip_rows, c1=cs, gate=masks["S3"], pixels=pix4, count=off4[n:],
                                    m_in0=off2[n:], m_in1=_pm(lambda: masks["S3"].sum()))
@@ -223,6 +256,8 @@ class _WaveDecoderBase(nn.Module):
                 prev_map = map4
             else:
                 xa = ops.conv_rows(x_rows, x_c, wp0, b0, c, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, map0=prev_map)
+                if skip_done is not None:
+                    torch.cuda.current_stream(dev).wait_event(skip_done)
                 xb = ops.conv_rows(xa, c, wp1, b1, c, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_ELU, shift0=1,
                                    x1=skip_rows, c1=cs)
                 t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1)

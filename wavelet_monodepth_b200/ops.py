@@ -228,19 +228,64 @@ def pad4(c):
     return (int(c) + 3) // 4 * 4
 
 
-def nchw_to_rows(x, ld=None):
-    """(N,C,H,W) -> rows (N*H*W, ld) pixel-major.  Zero-copy when x is channels_last and C % 4 == 0."""
+def nchw_to_rows(x, ld=None, stream=None, gate=None):
+    """(N,C,H,W) -> rows (N*H*W, ld) pixel-major.  Zero-copy when x is channels_last and C % 4 == 0.
+
+    gate: optional uint8 (N,1,H,W) / (N,H,W) mask of the pixels whose rows will be read later: only those rows are
+    produced (wmd_nchw_to_rows_gated_f32); the other rows of the result are uninitialised memory.
+    With a gate, x may also be a PINNED HOST tensor: the kernel then reads the marked parts of the map straight out of
+    host memory (zero-copy over PCIe) - the host->device transfer of a skip map shrinks with the mask density.
+    stream: optional side stream to run the transpose on (it first waits for the current stream, so `x` / `gate` may
+    have been produced there).  Then returns (rows, event): the consumer stream must wait for `event` (None when no
+    kernel was needed).  The output is allocated on the current stream, whose later work is what reads it."""
     lib = _lib.load()
     n, c, h, w = x.shape
     ld = pad4(c) if ld is None else ld
-    if x.dtype == _f32 and ld == c and x.permute(0, 2, 3, 1).is_contiguous() and x.data_ptr() % 16 == 0:
-        return x.permute(0, 2, 3, 1).reshape(n * h * w, c)
-    x = _dense(x)
-    rows = torch.empty((n * h * w, ld), dtype=_f32, device=x.device)
-    with _prof('nchw_to_rows', lambda: dict(n=n, c=c, hw=h * w, ld=ld)):
-        rc = lib.wmd_nchw_to_rows_f32(_lib.ptr(x), _lib.ptr(rows), n, c, h * w, ld, _lib.stream_ptr())
-    _lib.check(rc, "wmd_nchw_to_rows_f32")
-    return rows
+    on_host = not x.is_cuda
+    if on_host:
+        if gate is None:
+            raise _lib.WmdError("nchw_to_rows: a host feature map needs a gate (only the gated move reads host memory)")
+        if x.dtype != _f32 or not x.is_contiguous() or x.data_ptr() % 16:
+            raise _lib.WmdError("nchw_to_rows: host feature maps must be contiguous fp32 NCHW, 16-byte aligned")
+        dev = gate.device
+    else:
+        dev = x.device
+        if x.dtype == _f32 and ld == c and x.permute(0, 2, 3, 1).is_contiguous() and x.data_ptr() % 16 == 0:
+            rows = x.permute(0, 2, 3, 1).reshape(n * h * w, c)
+            return (rows, None) if stream is not None else rows
+        x = _dense(x)
+    if gate is not None:
+        gate = _dense(gate, _u8)
+        if gate.numel() != n * h * w:
+            raise _lib.WmdError("nchw_to_rows: gate of %d pixels for a %dx%dx%d map" % (gate.numel(), n, h, w))
+    rows = torch.empty((n * h * w, ld), dtype=_f32, device=dev)
+
+    def launch():
+        marked = _pm_count(gate)
+        with _prof('nchw_to_rows', lambda: dict(n=n, c=c, hw=h * w, ld=ld, marked=marked, host=on_host)):
+            if gate is None:
+                rc = lib.wmd_nchw_to_rows_f32(_lib.ptr(x), _lib.ptr(rows), n, c, h * w, ld, _lib.stream_ptr())
+            else:
+                rc = lib.wmd_nchw_to_rows_gated_f32(_lib.host_ptr(x, _f32), _lib.ptr(rows), _lib.ptr(gate), n, c, h * w, ld,
+                                                    _lib.stream_ptr())
+        _lib.check(rc, "wmd_nchw_to_rows_f32")
+
+    if stream is None:
+        launch()
+        return rows
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(stream):
+        launch()
+        done = torch.cuda.Event()
+        done.record(stream)
+    return rows, done
+
+
+def _pm_count(gate):
+    """Marked-pixel count of a gate for the profiler's byte accounting (None when not profiling or not gated)."""
+    if gate is None or _profiler is None:
+        return None
+    return gate.sum()
 
 
 def rows_to_nchw(rows, n, c, h, w):
