@@ -39,6 +39,8 @@ WORKLOADS = {
     "kitti_r50_1024x320_bs32": dict(ch=synth.RESNET50_CH, height=320, width=1024, per_gpu_batch=32),
     "kitti_r18_640x192_bs16": dict(ch=synth.RESNET18_CH, height=192, width=640, per_gpu_batch=16),
 }
+NYU = dict(name="nyu_d161_640x480_bs8", ch=synth.DENSENET161_CH, height=480, width=640, per_gpu_batch=8, thresh=0.1,
+           heads=["wave1.conv.", "wave2.conv.", "wave3.conv."], param_seed=11, feat_seed=2000)   # configs[3]
 MAIN = "kitti_r50_1024x320_bs32"
 ALSO = "kitti_r18_640x192_bs16"
 HEAD_KEYS = ["decoder.%d.2.conv." % k for k in (3, 4, 7, 8, 11, 12, 15, 16)]   # +/- coefficient heads' 3x3 stage
@@ -152,6 +154,10 @@ def account(name, info):
         n, h, w, g, cout = (info[k] for k in ("n", "h", "w", "groups", "cout"))
         m = min(_as_int(info["count"], n * h * w), info["max_rows"])
         return 4 * m * (9 * g + cout) + (n * h * w if info["count"] is not None else 0), 9 * g * m
+    if name == "head_mlp":
+        m = min(_as_int(info["count"], info["max_rows"]), info["max_rows"])
+        c, n1, nz = info["c"], info["n1"], info["nz"]
+        return 4 * m * (c + 56) + 4 * (n1 * c + nz * n1 + n1), 2 * m * (c * n1 + n1 * nz)
     if name == "head_conv3x3":
         n, h, w, c, cout = (info[k] for k in ("n", "h", "w", "c", "cout"))
         m = min(_as_int(info["count"], n * h * w), info["max_rows"])
@@ -585,6 +591,36 @@ def run_native(args, rank, world, local_rank):
                 "wavelet_mask_density": {str(s): round(float(o2[("wavelet_mask", s)].float().mean()), 4) for s in (3, 2, 1, 0)},
                 "total_ops_per_frame": o2["total_ops"] / wl2["per_gpu_batch"]}
 
+    # ---- 4b. NYUv2 workload of configs[3]: DenseNet161 pyramid 640x480, 8 frames/GPU, SparseDecoderWave thr 0.1
+    also_nyu = None
+    if args.workload == MAIN and not args.no_also:
+        from wavelet_monodepth_b200 import nyu_decoders
+        torch.cuda.empty_cache()
+        nmod = nyu_decoders.SparseDecoderWave(enc_features=list(NYU["ch"]), decoder_width=0.5)
+        synth.load_random(nmod, seed=NYU["param_seed"], gains={k: SYNTH["head_gain"] for k in NYU["heads"]},
+                          highpass=NYU["heads"])
+        nmod = nmod.to(dev).eval()
+        nb = NYU["per_gpu_batch"]
+        nfeats = [f.to(dev) for f in synth.blocky_features(
+            synth.nyu_feature_shapes(nb, NYU["height"], NYU["width"], NYU["ch"]), seed=NYU["feat_seed"] + rank * nb,
+            cell=SYNTH["cell"], texture=SYNTH["texture"])]
+        n3 = nb * world
+
+        def step3():
+            o = nmod(nfeats, NYU["thresh"])
+            if world > 1:
+                shard.all_gather_batch(o[("disp", 0)], n3)
+            last["out3"] = o
+
+        ms3 = time_device(step3, args.steps, max(args.warmup, 3), dist, world)
+        o3 = last["out3"]
+        also_nyu = {"workload": NYU["name"], "value": round(n3 * args.steps / (ms3 * 1e-3), 1), "unit": UNIT,
+                    "ms_per_step": round(ms3 / args.steps, 3), "global_batch": n3, "thresh_ratio": NYU["thresh"],
+                    "launch_mode": "eager", "decoder": "SparseDecoderWave (NYUv2/networks/decoders/densedepth_decoder.py:224-409), batched",
+                    "wavelet_mask_density": {str(s_): round(float(o3[("wavelet_mask", s_)].float().mean()), 4) for s_ in (2, 1, 0)},
+                    "total_ops_per_frame": o3["total_ops"] / nb, "dense_total_ops_per_frame": 33463546800}
+        del nmod, nfeats
+
     # ---- 5. CPU baseline (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -615,6 +651,7 @@ def run_native(args, rank, world, local_rank):
                 "timed_region": "decoder forward on NCHW fp32 features resident in HBM, incl. layout transposes, "
                                 "mask/compaction, the total_ops count read-back and (N>1) the all-gather",
                 "launch_mode": "CUDA graph replay (graphs.GraphedSparseDecoder)" if use_graph else "eager",
+                "head_1x1_stages": "fused (head_mlp) on levels 2, 1" if dec.fused_heads else "two gather-GEMM launches per level",
                 "layout_moves": "%s, %s" % ("gated by the upsample mask" if dec.gated_layout else "whole maps",
                                             "side stream" if dec.overlap_layout else "in order"),
             },
@@ -633,6 +670,7 @@ def run_native(args, rank, world, local_rank):
             "conv_layers": conv_layers,
             "cpu_baseline": cpu,
             "also": also,
+            "also_nyu": also_nyu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -135,6 +135,19 @@ int wmd_scatter_rows_nchw_f32(const float* rows, int ld, int C, const int32_t* p
 /* conv weight (Cout,Cin,kh,kw) -> packed [kh*kw][Cin][ldw] (ldw >= Cout, multiple of 4, pad zero) */
 int wmd_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, int taps, int ldw, wmd_stream_t stream);
 
+/* ---------------------------------------------------------------- fused 1x1 head stages
+ * z = Wz . lrelu(W1 . x + b1): the 1x1 stages of a level's + / - coefficient heads (Conv1x1 + LeakyReLU(0.1),
+ * depth_decoder.py:111-120) chained with the per-row tap products of their 3x3 stages (the 9 x 6 values
+ * wmd_head_gather_f32 sums per pixel).  x rows (M, c), W1 (n1, c), Wz (nz <= 56, n1); z rows (M, ldz >= 56), columns
+ * nz..55 are written as zeros.  The intermediate (M, n1) never reaches memory.  Supported (c, n1): (32, 64), (64, 128);
+ * other shapes return WMD_ERR_UNSUPPORTED (the caller then runs the two stages as wmd_conv_rows launches). */
+int wmd_head_mlp_supported(int c, int n1);
+size_t wmd_head_mlp_weight_floats(int c, int n1);
+int wmd_pack_head_mlp_f32(const float* w1, const float* wz, const float* b1, int c, int n1, int nz, float* packed,
+                          wmd_stream_t stream);
+int wmd_head_mlp_f32(const float* x, int ldx, int c, const float* packed, int n1, float slope, const int32_t* count,
+                     int max_rows, float* z, int ldz, wmd_stream_t stream);
+
 /* ---------------------------------------------------------------- gather-GEMM convolution
  * Replaces sparse_conv3x3 / sparse_conv1x1 / sparse_upsample / sparse_select (KITTI/layers.py:337-508,
  * NYUv2/networks/layers.py:82-223) and, with pixels == NULL, the dense Conv3x3/ConvBlock/Conv1x1 layers

@@ -383,3 +383,32 @@ def test_gated_layout_move_writes_exactly_the_marked_rows(n, c, h, w, p):
     assert bool((rows[~on] == -7.0).all())
     got = ops.nchw_to_rows(x, gate=gate)                     # wrapper (fresh buffer): marked rows only are defined
     assert torch.equal(got[on], want[on])
+
+
+@pytest.mark.parametrize("c,rows,count", [(32, 1000, None), (64, 777, None), (32, 4096, 3001), (64, 300, 0), (64, 20000, 19999),
+                                          (32, 15, 15)])
+def test_fused_head_mlp_vs_torch(c, rows, count):
+    """wmd_head_mlp_f32: z = Wz . lrelu(W1 . x + b1) (the 1x1 stages of the +/- heads chained with the tap products)
+    against fp64 torch; rows past `count` are not produced."""
+    n1, nz = 2 * c, 54
+    x = rnd(rows, c, seed=c + rows)
+    w1 = rnd(n1, c, 1, 1, seed=1, lo=-0.3, hi=0.3)
+    b1 = rnd(n1, seed=2, lo=-0.2, hi=0.2)
+    wz = rnd(nz, n1, 1, 1, seed=3, lo=-0.3, hi=0.3)
+    assert ops.head_mlp_supported(c, n1) and not ops.head_mlp_supported(128, 256)
+    packed = ops.pack_head_mlp(w1.to(DEV), b1.to(DEV), wz.to(DEV))
+    cnt = torch.tensor([count], dtype=torch.int32, device=DEV) if count is not None else None
+    z = ops.head_mlp(x.to(DEV), c, packed, n1, 0.1, count=cnt, max_rows=rows)
+    m = rows if count is None else count
+    t = F.leaky_relu(x.double() @ w1.double().reshape(n1, c).T + b1.double(), 0.1)
+    want = (t @ wz.double().reshape(nz, n1).T).float()
+    assert z.shape == (rows, 56)
+    if m:
+        assert rel_err(z[:m, :nz].cpu(), want[:m]) <= 1e-5
+        assert bool((z[:m, nz:] == 0).all())
+    # same numbers as the two-launch path it replaces (both engines are fp32-faithful)
+    if m:
+        wp = ops.pack_weight(w1.to(DEV), kind="simt")
+        t2 = ops.conv_rows(x.to(DEV), c, wp, b1.to(DEV), n1, 1, 1, rows, taps=1, act=ACT_LRELU, act_param=0.1)
+        z2 = ops.conv_rows(t2, n1, ops.pack_weight(wz.to(DEV), kind="simt"), None, nz, 1, 1, rows, taps=1)
+        assert rel_err(z[:m, :nz], z2[:m, :nz]) <= 1e-5

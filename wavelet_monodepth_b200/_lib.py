@@ -76,6 +76,11 @@ SIGNATURES = {
     "wmd_scatter_rows_nchw_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                           c_int, c_void_p]),
     "wmd_pack_conv_weight_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "wmd_head_mlp_supported": (c_int, [c_int, c_int]),
+    "wmd_head_mlp_weight_floats": (c_size_t, [c_int, c_int]),
+    "wmd_pack_head_mlp_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "wmd_head_mlp_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, c_int,
+                                 c_void_p]),
     "wmd_conv_rows_f32": (c_int, [POINTER(ConvDesc), c_void_p]),
     "wmd_conv_tc_tile_n": (c_int, [c_int]),
     "wmd_conv_tc_weight_floats": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -83,8 +83,15 @@ constexpr int kTraceChunks = 256, kTraceSlots = 8;
 __device__ long long g_trace[3 * kTraceSlots * kTraceChunks];
 #define TC_TRACE(role, slot, c) do { if (blockIdx.x == 0 && lane == 0 && (c) < kTraceChunks) \
     g_trace[((role) * kTraceSlots + (slot)) * kTraceChunks + (c)] = clock64(); } while (0)
+// per-tile timeline of CTA 0 (thread 0 = split warp 0): tile top, tables built, first raw A landed, chunk loop done,
+// last epoch complete, drained, stored, end-of-tile barrier passed
+constexpr int kTraceTiles = 64, kTileSlots = 8;
+__device__ long long g_tile_trace[kTraceTiles * kTileSlots];
+#define TC_TILE_TRACE(slot) do { if (blockIdx.x == 0 && tid == 0 && tile_iter < kTraceTiles) \
+    g_tile_trace[tile_iter * kTileSlots + (slot)] = clock64(); } while (0)
 #else
 #define TC_TRACE(role, slot, c) do {} while (0)
+#define TC_TILE_TRACE(slot) do {} while (0)
 #endif
 // bounded spin: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t id = 0) {
@@ -306,7 +313,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   const long long u_end = balanced ? min(rem_units, u + U) : 0;
   long long item = blockIdx.x;
   const long long items = balanced ? rem_tile0 : tiles * splits;
+  int tile_iter = -1;
   while (true) {
+    ++tile_iter;
     long long tile;
     int cb, ce, slab;
     bool whole;
@@ -337,6 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     const int m0 = static_cast<int>(tile / n_tiles) * TC_BM;
     const int nt = static_cast<int>(tile % n_tiles);
     const int n0 = nt * BN;
+    TC_TILE_TRACE(0);
 
     for (int e = tid; e < d.taps * TC_BM; e += TC_THREADS) {
       const int tap = e / TC_BM, r = e - tap * TC_BM;
@@ -371,6 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       tab1[e] = o1;
     }
     __syncthreads();
+    TC_TILE_TRACE(1);
 
     const unsigned char* wtile = reinterpret_cast<const unsigned char*>(wtc) +
                                  static_cast<long long>(nt) * nchunks * (2 * TC_B_TILE);
@@ -476,6 +487,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         if (warp == 0) TC_TRACE(0, 0, c);
         mbar_wait(smem_u32(&bar_raw_full[rs]), (round / TC_A_STAGES) & 1, 0x20000u + round);
         if (warp == 0) TC_TRACE(0, 1, c);
+        if (c == 0) TC_TILE_TRACE(2);
         // TMEM A stage free?  It was read by the MMAs of round-2.
         if (round >= 2) mbar_wait(smem_u32(&bar_mma[ts]), ((round - 2) >> 1) & 1, 0x28000u + round);
         tc_fence_after();
@@ -593,12 +605,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       }
     }
     mma_rounds = round0 + static_cast<uint32_t>(len);
+    TC_TILE_TRACE(3);
 
     // ---- last epoch + epilogue (all 16 warps): bias, activation, one contiguous 256-byte store per thread
     {
       mbar_wait(smem_u32(&bar_epoch), (epochs - 1) & 1, 0x60000u + mma_rounds);
       tc_fence_after();
+      TC_TILE_TRACE(4);
       drain();
+      TC_TILE_TRACE(5);
       const int m = m0 + my_row;
       if (m < rows && !whole) {
         // raw partial sums of this segment (bias / activation are applied by the reduce pass)
@@ -638,9 +653,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         }
       }
     }
+    TC_TILE_TRACE(6);
     tc_fence_before();
     __syncthreads();   // accumulators drained + re-zeroed by every warp, tap tables free
     tc_fence_after();
+    TC_TILE_TRACE(7);
   }
 
   __syncthreads();
@@ -815,6 +832,9 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
 #ifdef WMD_TC_TRACE
 extern "C" int wmd_debug_tc_trace(long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, wmd::g_trace, sizeof(wmd::g_trace)) == cudaSuccess ? 0 : 1;
+}
+extern "C" int wmd_debug_tc_tile_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, wmd::g_tile_trace, sizeof(wmd::g_tile_trace)) == cudaSuccess ? 0 : 1;
 }
 #endif
 

@@ -149,6 +149,8 @@ class _WaveDecoderBase(nn.Module):
         self.overlap_layout = os.environ.get("WMD_OVERLAP_LAYOUT", "0") == "1"
         # transpose a sparse level's skip map only under its upsample mask (WMD_GATED_LAYOUT=0/1 sets the default)
         self.gated_layout = os.environ.get("WMD_GATED_LAYOUT", "0") == "1"
+        # run the two 1x1 head stages of the fine levels as one fused kernel (WMD_FUSED_HEADS=0/1 sets the default)
+        self.fused_heads = os.environ.get("WMD_FUSED_HEADS", "1") == "1"
 
     # ---- packed parameters ------------------------------------------------------------------
     def _upconv(self, i, j):
@@ -181,6 +183,18 @@ class _WaveDecoderBase(nn.Module):
         bz = self._packs.get(("headtapsb", i), [cp.bias, cn.bias],
                              lambda: torch.cat([cp.bias.detach(), cn.bias.detach()]).contiguous())
         return wz, bz
+
+    def _head_mlp(self, i):
+        """Fused 1x1 stages of the + / - heads (levels without an LL head): packed [W1 | Wz | b1] image or None."""
+        c = int(self.num_ch_dec[i])
+        if i == 4 or not self.fused_heads or not ops.head_mlp_supported(c, 2 * c):
+            return None
+        c1p, c1n = self.convs[("waveconv", i, 1)][0].conv, self.convs[("waveconv", i, -1)][0].conv
+        c3p, c3n = self.convs[("waveconv", i, 1)][2].conv, self.convs[("waveconv", i, -1)][2].conv
+        return self._packs.get(("headmlp", i), [c1p.weight, c1n.weight, c1p.bias, c1n.bias, c3p.weight, c3n.weight],
+                               lambda: ops.pack_head_mlp(torch.cat([c1p.weight.detach(), c1n.weight.detach()], 0),
+                                                         torch.cat([c1p.bias.detach(), c1n.bias.detach()], 0),
+                                                         ops.head_tap_weight([c3p.weight, c3n.weight], [0, c], 2 * c)))
 
     def _head_3x3(self, i, j):
         conv = self.convs[("waveconv", i, j)][2].conv
@@ -235,6 +249,8 @@ class _WaveDecoderBase(nn.Module):
             wp0, b0 = self._upconv(i, 0)
             wp1, b1 = self._upconv(i, 1)
             w1x1, b1x1, offs, c1x1 = self._head_1x1(i)
+            mlp = self._head_mlp(i)                      # fused 1x1 stages (then t is never materialised)
+            t = None
             if sparse:
                 if yl is None:
                     raise WmdError("a sparse level needs a previous dense level (depth_decoder.py:344)")
@@ -250,8 +266,9 @@ class _WaveDecoderBase(nn.Module):
                 xb = ops.conv_rows(xa, c, wp1, b1, c, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_ELU, map0=map2,
                                    shift0=1, x1=skip_rows, c1=cs, gate=masks["S3"], pixels=pix4, count=off4[n:],
                                    m_in0=off2[n:], m_in1=_pm(lambda: masks["S3"].sum()))
-                t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1,
-                                  pixels=pix4, count=off4[n:], m_in0=off4[n:])
+                if mlp is None:
+                    t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1,
+                                      pixels=pix4, count=off4[n:], m_in0=off4[n:])
                 head_kw = dict(idxmap=map4, pixels=pix5, count=off5[n:])
                 prev_map = map4
             else:
@@ -260,7 +277,8 @@ class _WaveDecoderBase(nn.Module):
                     torch.cuda.current_stream(dev).wait_event(skip_done)
                 xb = ops.conv_rows(xa, c, wp1, b1, c, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_ELU, shift0=1,
                                    x1=skip_rows, c1=cs)
-                t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1)
+                if mlp is None:
+                    t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1)
                 head_kw = {}
                 if with_masks and i != 4:
                     # dense level under a thresholded mask: yh * wavelet_mask (depth_decoder.py:271-272)
@@ -273,7 +291,9 @@ class _WaveDecoderBase(nn.Module):
                                       act=ACT_SIGMOID, pad=PAD_REFLECT)
             # +/- heads, factored: per-row tap products on the GEMM engine, then a 9 x 6 float gather-sum per pixel
             wz, bz = self._head_taps(i, offs, c1x1)
-            if sparse:
+            if mlp is not None:
+                z = ops.head_mlp(xb, c, mlp, c1x1, 0.1, count=off4[n:] if sparse else None, max_rows=n * 4 * h * w)
+            elif sparse:
                 z = ops.conv_rows(t, c1x1, wz, None, 54, n, 2 * h, 2 * w, taps=1, pixels=pix4, count=off4[n:], m_in0=off4[n:])
             else:
                 z = ops.conv_rows(t, c1x1, wz, None, 54, n, 2 * h, 2 * w, taps=1)

@@ -438,6 +438,39 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
     return out
 
 
+def head_mlp_supported(c, n1):
+    return bool(_lib.load().wmd_head_mlp_supported(int(c), int(n1)))
+
+
+def pack_head_mlp(w1, b1, wz):
+    """(n1, c, 1, 1) 1x1 weight, (n1,) bias, (nz, n1, 1, 1) tap-product weight -> packed image for head_mlp."""
+    lib = _lib.load()
+    w1, wz = _dense(w1.detach()), _dense(wz.detach())
+    n1, c, nz = int(w1.shape[0]), int(w1.shape[1]), int(wz.shape[0])
+    if int(wz.shape[1]) != n1:
+        raise _lib.WmdError("pack_head_mlp: wz expects %d inputs, w1 produces %d" % (wz.shape[1], n1))
+    nfl = lib.wmd_head_mlp_weight_floats(c, n1)
+    if nfl == 0:
+        raise _lib.WmdError("head_mlp: unsupported shape c=%d n1=%d" % (c, n1))
+    packed = torch.empty((nfl,), dtype=_f32, device=w1.device)
+    rc = lib.wmd_pack_head_mlp_f32(_lib.ptr(w1), _lib.ptr(wz), _lib.ptr(_dense(b1.detach()) if b1 is not None else None),
+                                   c, n1, nz, _lib.ptr(packed), _lib.stream_ptr())
+    _lib.check(rc, "wmd_pack_head_mlp_f32")
+    return packed
+
+
+def head_mlp(x, c, packed, n1, slope=0.1, count=None, max_rows=None, nz=54):
+    """z (max_rows, 56) = Wz . lrelu(W1 . x + b1) on pixel-major rows x (R, ld >= c); see wmd_head_mlp_f32."""
+    lib = _lib.load()
+    max_rows = x.shape[0] if max_rows is None else int(max_rows)
+    z = torch.empty((max(max_rows, 1), 56), dtype=_f32, device=x.device)
+    with _prof('head_mlp', lambda: dict(c=c, n1=n1, nz=nz, count=count, max_rows=max_rows)):
+        rc = lib.wmd_head_mlp_f32(_lib.ptr(x, _f32), x.shape[1], c, _lib.ptr(packed, _f32), n1, float(slope),
+                                  _lib.ptr(count, _i32), max_rows, _lib.ptr(z), 56, _lib.stream_ptr())
+    _lib.check(rc, "wmd_head_mlp_f32")
+    return z
+
+
 def head_conv3x3(t, c, off_a, wa, ba, n, h, w, cout, scale=1.0, act=ACT_NONE, pad=PAD_REFLECT, off_b=-1, wb=None,
                  bb=None, idxmap=None, pixels=None, count=None, max_rows=None, out=None):
     """3x3 stage of the coefficient heads -> dense (N,cout,H,W); see wmd_head_conv3x3_f32.
