@@ -30,7 +30,6 @@
 // tensor-pipe work.  The earlier cp.async gather cost ~640 wavefronts per chunk on top and serialised with the split.
 // TMEM map (512 columns): [0,2N) accumulators (half h at h*N), [256,512) A operand: stage s, half h at
 // 256 + s*128 + h*64, hi in the first 32 columns, lo in the next 32.
-#include <cstdlib>
 #include <cuda.h>   // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
 
 #include "common.cuh"
@@ -43,12 +42,7 @@ constexpr int TC_THREADS = 512;                 // 16 warps: 8 split + 6 gather 
 constexpr int TC_SPLIT_WARPS = 8;               // warps 0-7: warp w owns tile rows (w>>2)*128 + (w&3)*32 + lane (its TMEM lane quarter)
 constexpr int TC_GATHER_WARPS = 6;              // warps 8-13
 constexpr int TC_ISSUERS = 2;                   // warps 14-15: one per M half, each the only writer of its accumulator
-constexpr int TC_A_STAGES = 3;                  // raw A stages, one-tap groups: 3 x 32 KB (two gathers in flight + one being split)
-constexpr int TC_SH_STAGES = 2;                 // raw A stages, shared three-tap groups: 2 x 40 KB (same 96 KB)
-constexpr int TC_SH_SLOTS = 320;                // rows of a shared stage: 256 centre-tap sources + zero row + 63 extras
-constexpr int TC_SH_TILE = TC_SH_SLOTS * TC_BK * 4;
-constexpr int TC_SH_ZERO = TC_BM;               // slot whose source is "no row": the TMA zero-fills it
-constexpr int TC_SH_EXTRA0 = TC_BM + 1;         // first extra slot
+constexpr int TC_A_STAGES = 3;                  // raw A tiles in shared memory (two gathers in flight + one being split)
 constexpr int TC_T_STAGES = 2;                  // split A stages in tensor memory
 constexpr int TC_B_STAGES = 3;                  // [Bhi | Blo] images in shared memory
 constexpr int TC_A_TILE = TC_BM * TC_BK * 4;    // 32 KB raw fp32
@@ -225,8 +219,7 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_conv_desc d, const float* __restrict__ wtc,
                                                                      const int splits, float* __restrict__ partial,
                                                                      const __grid_constant__ CUtensorMap tm0,
-                                                                     const __grid_constant__ CUtensorMap tm1,
-                                                                     const int share_in) {
+                                                                     const __grid_constant__ CUtensorMap tm1) {
   using Cfg = TcCfg<BN>;
   constexpr int TC_B_TILE = Cfg::B_TILE;
   constexpr int ACC = Cfg::ACC;
@@ -238,8 +231,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   __shared__ __align__(8) uint64_t bar_b[TC_B_STAGES];     // weight image of the stage has landed (bulk copy)
   __shared__ __align__(8) uint64_t bar_epoch;              // accumulation epoch complete (4 issuers)
   __shared__ uint32_t tmem_base_slot;
-  __shared__ int sh_extra[6];                               // shared groups: extra slots in use, per (source, dy)
-  __shared__ int sh_overflow;                               // ... this tile needs more extras than a stage holds
 
   // warp index through a shuffle: provably warp-uniform, so the role branches and everything the issuer warps
   // compute from it stay on the uniform datapath (see the issuer section)
@@ -249,14 +240,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   unsigned char* sB_base = base + TC_A_STAGES * TC_A_TILE;
   int32_t* tab0 = reinterpret_cast<int32_t*>(sB_base + TC_B_STAGES * 2 * TC_B_TILE);   // [tap][row]: source row in x0, -1 = none
   int32_t* tab1 = tab0 + 9 * TC_BM;                                                    // ... in x1
-  // shared three-tap groups use the same 18 KB differently: source lists [src][dy][slot] + slot tables [src][tap][row]
-  int32_t* sh_list = tab0;
-  uint16_t* sh_slot = reinterpret_cast<uint16_t*>(tab0 + 2 * 3 * TC_SH_SLOTS);
-  static_assert(2 * 3 * TC_SH_SLOTS * 4 + 2 * 9 * TC_BM * 2 <= TC_TABLES, "shared-group tables fit the tap-table region");
-  static_assert(TC_SH_STAGES * TC_SH_TILE <= TC_A_STAGES * TC_A_TILE && TC_SH_TILE % 1024 == 0, "shared stages fit the raw region");
-  const bool share = share_in != 0 && d.taps == 9;
-  const uint32_t nstg = share ? TC_SH_STAGES : TC_A_STAGES;
-  const uint32_t stg_bytes = share ? TC_SH_TILE : TC_A_TILE;
 
   if (tid == 0) {
     for (int s = 0; s < TC_A_STAGES; ++s) {
@@ -303,7 +286,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   const uint32_t lane_field = static_cast<uint32_t>(my_q * 32) << 16;
   const uint32_t my_acc_addr = tmem_acc + lane_field + static_cast<uint32_t>(my_half * BN + my_ch * ACC);
   uint32_t mma_rounds = 0;                                       // chunks issued so far by this CTA (all tiles)
-  uint32_t grp_rounds = 0;                                       // raw-stage groups gathered so far (all tiles)
   uint32_t epochs = 0;                                           // epoch commits so far
 
   // accumulators start (and are left by every drain) at zero: every MMA accumulates
@@ -366,102 +348,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     const int n0 = nt * BN;
     TC_TILE_TRACE(0);
 
-    // ---- per-tile source tables ------------------------------------------------------------------------------
-    // source_of(row, tap) -> row index in x0 / x1 (kNoRow = the tap reads zeros): pixel list, border rule, gate, index map
-    auto source_of = [&](int r, int tap, int32_t& o0, int32_t& o1) {
-      o0 = kNoRow; o1 = kNoRow;
+    for (int e = tid; e < d.taps * TC_BM; e += TC_THREADS) {
+      const int tap = e / TC_BM, r = e - tap * TC_BM;
       const int m = m0 + r;
-      if (m >= rows) return;
-      const int p = d.pixels ? d.pixels[m] : m;
-      const int n = static_cast<int>(p / HW);
-      const int rem = static_cast<int>(p - n * HW);
-      const int y = rem / d.W, x = rem - y * d.W;
-      int qy = y, qx = x;
-      if (d.taps == 9) { qy += tap / 3 - 1; qx += tap % 3 - 1; }
-      bool ok = pad_coord(qy, d.H, d.pad_mode);
-      ok = pad_coord(qx, d.W, d.pad_mode) && ok;
-      if (!ok) return;
-      const int q = (n * d.H + qy) * d.W + qx;
-      if (d.gate && !d.gate[q]) return;
-      o1 = q;
-      int r0;
-      if (aligned_rows) {
-        r0 = m;
-      } else {
-        const int qs = (n * Hs + (qy >> d.shift0)) * Ws + (qx >> d.shift0);
-        r0 = d.map0 ? d.map0[qs] : qs;
-      }
-      if (r0 >= 0) o0 = r0;
-    };
-    // Shared three-tap groups (3x3 layers): the sources of taps (dy,-1), (dy,0), (dy,+1) of neighbouring output rows
-    // are mostly the same rows shifted by one, so one raw stage per (dy, channel chunk) holds the centre-tap sources of
-    // the 256 rows (slot = row), a zero row, and up to 63 "extra" rows for side-tap sources that are not a neighbour's
-    // centre source (ends of runs of active pixels); slot[src][tap][row] says where each tap finds its row.  One gather
-    // of <= 80 loads then feeds three chunks instead of three gathers of 64.  A tile that needs more extras than fit
-    // (very ragged masks) falls back to one-tap groups with the plain [tap][row] tables.
-    int gs = 1;                                              // chunks served by one raw stage in this tile
-    if (share) {
-      if (tid < 6) sh_extra[tid] = 0;
-      if (tid == 6) sh_overflow = 0;
-      for (int e = tid; e < 3 * TC_SH_SLOTS; e += TC_THREADS) {
-        const int dy = e / TC_SH_SLOTS, sl = e - dy * TC_SH_SLOTS;
-        int32_t o0 = kNoRow, o1 = kNoRow;
-        if (sl < TC_BM) source_of(sl, dy * 3 + 1, o0, o1);
-        sh_list[(0 * 3 + dy) * TC_SH_SLOTS + sl] = o0;
-        sh_list[(1 * 3 + dy) * TC_SH_SLOTS + sl] = o1;
-      }
-      __syncthreads();
-      for (int e = tid; e < 9 * TC_BM; e += TC_THREADS) {
-        const int tap = e / TC_BM, r = e - tap * TC_BM;
-        const int dy = tap / 3;
-        if (tap % 3 == 1) {                                  // centre tap: its own slot (a kNoRow source is zero-filled there)
-          sh_slot[(0 * 9 + tap) * TC_BM + r] = static_cast<uint16_t>(r);
-          sh_slot[(1 * 9 + tap) * TC_BM + r] = static_cast<uint16_t>(r);
-          continue;
-        }
-        int32_t o[2];
-        source_of(r, tap, o[0], o[1]);
-#pragma unroll
-        for (int sidx = 0; sidx < 2; ++sidx) {
-          if (sidx == 1 && d.c1 == 0) { sh_slot[(9 + tap) * TC_BM + r] = static_cast<uint16_t>(TC_SH_ZERO); continue; }
-          const int32_t* lst = sh_list + (sidx * 3 + dy) * TC_SH_SLOTS;
-          int sl = TC_SH_ZERO;
-          if (o[sidx] != kNoRow) {
-            if (lst[r] == o[sidx]) sl = r;
-            else if (r > 0 && lst[r - 1] == o[sidx]) sl = r - 1;
-            else if (r + 1 < TC_BM && lst[r + 1] == o[sidx]) sl = r + 1;
-            else {
-              const int ex = atomicAdd(&sh_extra[sidx * 3 + dy], 1);
-              if (ex < TC_SH_SLOTS - TC_SH_EXTRA0) {
-                sl = TC_SH_EXTRA0 + ex;
-                sh_list[(sidx * 3 + dy) * TC_SH_SLOTS + sl] = o[sidx];
-              } else {
-                sh_overflow = 1;
-              }
+      int32_t o0 = kNoRow, o1 = kNoRow;
+      if (m < rows) {
+        const int p = d.pixels ? d.pixels[m] : m;
+        const int n = static_cast<int>(p / HW);
+        const int rem = static_cast<int>(p - n * HW);
+        const int y = rem / d.W, x = rem - y * d.W;
+        int qy = y, qx = x;
+        if (d.taps == 9) { qy += tap / 3 - 1; qx += tap % 3 - 1; }
+        bool ok = pad_coord(qy, d.H, d.pad_mode);
+        ok = pad_coord(qx, d.W, d.pad_mode) && ok;
+        if (ok) {
+          const int q = (n * d.H + qy) * d.W + qx;
+          if (d.gate && !d.gate[q]) ok = false;
+          if (ok) {
+            o1 = q;
+            int r0;
+            if (aligned_rows) {
+              r0 = m;
+            } else {
+              const int qs = (n * Hs + (qy >> d.shift0)) * Ws + (qx >> d.shift0);
+              r0 = d.map0 ? d.map0[qs] : qs;
             }
+            if (r0 >= 0) o0 = r0;
           }
-          sh_slot[(sidx * 9 + tap) * TC_BM + r] = static_cast<uint16_t>(sl);
         }
       }
-      __syncthreads();
-      gs = sh_overflow ? 1 : 3;
-      if (gs == 1) __syncthreads();                          // everyone has read the flag before the tables are rebuilt
+      tab0[e] = o0;
+      tab1[e] = o1;
     }
-    if (gs == 1) {
-      for (int e = tid; e < d.taps * TC_BM; e += TC_THREADS) {
-        const int tap = e / TC_BM, r = e - tap * TC_BM;
-        int32_t o0, o1;
-        source_of(r, tap, o0, o1);
-        tab0[e] = o0;
-        tab1[e] = o1;
-      }
-      __syncthreads();
-    }
+    __syncthreads();
     TC_TILE_TRACE(1);
-    // groups of this segment: chunk c (segment-local) belongs to group (cb + c) / gs - cb / gs
-    const int grp_first = cb / gs;
-    const int ngroups = (ce - 1) / gs - grp_first + 1;
-    const uint32_t grp0 = grp_rounds;
 
     const unsigned char* wtile = reinterpret_cast<const unsigned char*>(wtc) +
                                  static_cast<long long>(nt) * nchunks * (2 * TC_B_TILE);
@@ -498,90 +418,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     };
 
     // Implicit im2col through the TMA: every `tile::gather4` load fetches the 128-byte channel slice of FOUR arbitrary
-    // source rows (row indices from the tile's source list; -1 and channels past C are zero-filled by the TMA) into 512
-    // contiguous, 128B-swizzled bytes of the raw stage and completes on the stage's mbarrier.  A one-tap group is 64
-    // loads, a shared three-tap group 64 + ceil((1 + extras) / 4); gather warp g issues loads g, g+6, ...  One load
-    // costs the issuing warp ~140 clk - that is the TMA unit's queue, not the warp: the unit sustains one gather4 per
-    // ~24 clk per SM, which is what bounded the N <= 64 layers before the three taps of a row shared one gather.
-    // Everything a load needs except the four row indices is made provably warp-uniform (shuffles), so ptxas keeps it
-    // in uniform registers across the unrolled loop; per load that leaves one LDS.128 + four R2URs.
-    constexpr int kMaxLoadsPerWarp = (TC_SH_SLOTS / 4 + TC_GATHER_WARPS - 1) / TC_GATHER_WARPS;
+    // source rows (row indices from the tap table; -1 and channels past C are zero-filled by the TMA) into 512
+    // contiguous, 128B-swizzled bytes of the raw stage and completes on the stage's mbarrier.  A chunk is 64 loads:
+    // gather warp g issues groups g, g+6, ...  One load costs the issuing warp ~140 clk here - that is the TMA unit's
+    // queue, not the warp: the unit sustains one gather4 per ~25-30 clk per SM next to the weight copies, i.e. the
+    // L2->SM path at ~9 TB/s aggregate (A 32 KB + B <= 32 KB per chunk per SM).  Letting the split warps issue part
+    // of the loads (kSplitGather > 0) was measured and does not help.  Everything a load needs except the four row
+    // indices is made provably warp-uniform (shuffles), so ptxas keeps it in uniform registers across the unrolled
+    // loop; per load that leaves one LDS.128 + four R2URs.
+    constexpr int kMaxLoadsPerWarp = (TC_BM / 4 + TC_GATHER_WARPS - 1) / TC_GATHER_WARPS;
     const uint32_t sA_u = __shfl_sync(0xffffffffu, smem_u32(sA_base), 0);
-    // g = segment-local group, R = its global group number (raw stage + barrier phase)
-    auto issue_group = [&](int g, uint32_t R) {
-      const int gw = warp - TC_SPLIT_WARPS;                     // 0..5
-      const int cg = (grp_first + g) * gs;                      // absolute chunk index of the group's first chunk
-      const int rr = cg / d.taps;
-      const int tap = cg - rr * d.taps;
+    auto issue_gathers = [&](int c, uint32_t round, int g0, int gstride, int gend, int nmax, bool expect) {
+      const uint32_t st = round % TC_A_STAGES;
+      const int rr = c / d.taps;                  // channel chunk outermost, taps innermost: the nine taps of a
+      const int tap = c - rr * d.taps;            // chunk re-read (almost) the same rows while they are hot in L2
       const bool src1 = rr >= nch0;
-      const uint32_t st = R % nstg;
-      int nquads = TC_BM / 4;
-      const int32_t* lst;
-      if (gs == 3) {
-        const int li = (src1 ? 3 : 0) + tap / 3;
-        lst = sh_list + li * TC_SH_SLOTS;
-        nquads = TC_BM / 4 + (1 + min(sh_extra[li], TC_SH_SLOTS - TC_SH_EXTRA0) + 3) / 4;
-      } else {
-        lst = (src1 ? tab1 : tab0) + tap * TC_BM;
-      }
-      nquads = __shfl_sync(0xffffffffu, nquads, 0);
       const int col = __shfl_sync(0xffffffffu, (src1 ? rr - nch0 : rr) * TC_BK, 0);
-      const uint32_t tab_u = __shfl_sync(0xffffffffu, smem_u32(lst + 4 * gw), 0);
+      const uint32_t tab_u = __shfl_sync(0xffffffffu, smem_u32((src1 ? tab1 : tab0) + tap * TC_BM + 4 * g0), 0);
       const uint64_t tmp = reinterpret_cast<uint64_t>(src1 ? &tm1 : &tm0);
       const uint64_t tm_u = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp >> 32), 0)) << 32) |
                             __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp), 0);
       const uint32_t bar = __shfl_sync(0xffffffffu, smem_u32(&bar_raw_full[st]), 0);
-      const uint32_t dst_u = __shfl_sync(0xffffffffu, sA_u + st * stg_bytes + gw * 512, 0);
-      if (gw == 0 && elect_one())
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(static_cast<uint32_t>(nquads * 512)) : "memory");
+      const uint32_t dst_u = __shfl_sync(0xffffffffu, sA_u + st * TC_A_TILE + g0 * 512, 0);
+      if (expect && elect_one())
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(static_cast<uint32_t>(TC_A_TILE)) : "memory");
 #pragma unroll
       for (int i = 0; i < kMaxLoadsPerWarp; ++i) {
-        if (gw + i * TC_GATHER_WARPS < nquads) {
+        if (i < nmax && g0 + i * gstride < gend) {
           int4 r4;
           asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n"
               : "=r"(r4.x), "=r"(r4.y), "=r"(r4.z), "=r"(r4.w)
-              : "r"(tab_u + static_cast<uint32_t>(i * TC_GATHER_WARPS * 16)));
+              : "r"(tab_u + static_cast<uint32_t>(i * gstride * 16)));
           if (elect_one())
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(
-                    dst_u + static_cast<uint32_t>(i * TC_GATHER_WARPS * 512)),
+                    dst_u + static_cast<uint32_t>(i * gstride * 512)),
                 "l"(tm_u), "r"(col), "r"(r4.x), "r"(r4.y), "r"(r4.z), "r"(r4.w), "r"(bar)
                 : "memory");
         }
       }
     };
+    constexpr int kSplitGather = 0;                                     // loads per split warp per chunk
+    constexpr int kGatherGroups = TC_BM / 4 - TC_SPLIT_WARPS * kSplitGather;   // groups left to the gather warps
+    static_assert(kGatherGroups <= kMaxLoadsPerWarp * TC_GATHER_WARPS, "issue_gathers unroll bound");
+    auto gather_chunk = [&](int c, uint32_t round) {                    // gather-warp share
+      issue_gathers(c, round, warp - TC_SPLIT_WARPS, TC_GATHER_WARPS, kGatherGroups, kMaxLoadsPerWarp, warp == TC_SPLIT_WARPS);
+    };
+    auto split_gather_chunk = [&](int c, uint32_t round) {              // split-warp share
+      issue_gathers(c, round, kGatherGroups + warp, TC_SPLIT_WARPS, TC_BM / 4, kSplitGather, false);
+    };
 
     if (warp < TC_SPLIT_WARPS) {
       // =================================================================================== split warps
       // raw fp32 row (128 B of the smem stage) -> hi / lo in tensor memory.  Thread = tile row `my_row` = TMEM lane.
+      if (kSplitGather > 0) {
+        split_gather_chunk(cb, round0);
+        if (len > 1) split_gather_chunk(cb + 1, round0 + 1);
+      }
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
-        const uint32_t ts = round & 1;
-        const int ca = cb + c;                                    // absolute chunk
-        const uint32_t R = grp0 + static_cast<uint32_t>(ca / gs - grp_first);
-        const uint32_t rs = R % nstg;
+        const uint32_t rs = round % TC_A_STAGES, ts = round & 1;
         epoch_boundary(c);
+        if (kSplitGather > 0 && c + 2 < len) {       // my share of the gather two chunks ahead (stage read by round-1: all 8 split warps done?)
+          const uint32_t r2 = round + 2, st2 = r2 % TC_A_STAGES;
+          if (c + 2 >= TC_A_STAGES) mbar_wait(smem_u32(&bar_raw_empty[st2]), ((r2 - TC_A_STAGES) / TC_A_STAGES) & 1, 0x38000u + round);
+          split_gather_chunk(cb + c + 2, r2);
+        }
         if (warp == 0) TC_TRACE(0, 0, c);
-        mbar_wait(smem_u32(&bar_raw_full[rs]), (R / nstg) & 1, 0x20000u + round);   // (re-)checks the group's phase: cheap
+        mbar_wait(smem_u32(&bar_raw_full[rs]), (round / TC_A_STAGES) & 1, 0x20000u + round);
         if (warp == 0) TC_TRACE(0, 1, c);
         if (c == 0) TC_TILE_TRACE(2);
         // TMEM A stage free?  It was read by the MMAs of round-2.
         if (round >= 2) mbar_wait(smem_u32(&bar_mma[ts]), ((round - 2) >> 1) & 1, 0x28000u + round);
         tc_fence_after();
         if (warp == 0) TC_TRACE(0, 2, c);
-        int slot = my_row;
-        if (gs == 3) {
-          const int rr = ca / 9;
-          slot = sh_slot[((rr >= nch0 ? 9 : 0) + (ca - rr * 9)) * TC_BM + my_row];
-        }
-        const unsigned char* rowp = sA_base + rs * stg_bytes + slot * 128;
+        const unsigned char* rowp = sA_base + rs * TC_A_TILE + my_row * 128;
         const uint32_t ta = tmem_acc + lane_field + 256u + ts * 128u + static_cast<uint32_t>(my_half * 64);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {              // 16 channels at a time
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4*>(rowp + (((4 * hf + q) ^ (slot & 7)) << 4));   // undo the TMA swizzle
+            const uint4 v = *reinterpret_cast<const uint4*>(rowp + (((4 * hf + q) ^ (my_row & 7)) << 4));   // swizzle: conflict-free
             const uint32_t raw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -593,8 +511,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           tmem_st16(ta + 32u + static_cast<uint32_t>(16 * hf), lo);
         }
         __syncwarp();
-        if (lane == 0 && (c == len - 1 || (ca + 1) % gs == 0))
-          mbar_arrive(smem_u32(&bar_raw_empty[rs]));                  // last chunk of the group: raw stage may be overwritten
+        if (lane == 0) mbar_arrive(smem_u32(&bar_raw_empty[rs]));      // raw stage may be overwritten
         if (warp == 0) TC_TRACE(0, 3, c);
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         tc_fence_before();
@@ -605,27 +522,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       }
     } else if (warp < TC_SPLIT_WARPS + TC_GATHER_WARPS) {
       // =================================================================================== gather warps
-      // nstg - 1 groups ahead of the split warps (two one-tap groups, or one shared three-tap group = three chunks).
-      // The raw stages are free at the start of a tile (every split of the previous tile has completed), so the first
-      // groups go out unconditionally; at the first chunk of group g, group g + ahead goes into the stage group g - 1
-      // used, once the 8 split warps have released it.  (Never wait for the CURRENT group here: its last chunk may sit
-      // behind an epoch boundary, a CTA-wide barrier this warp has to join.)
-      const int ahead = static_cast<int>(nstg) - 1;
-      for (int a = 0; a < ahead; ++a)
-        if (a < ngroups) issue_group(a, grp0 + static_cast<uint32_t>(a));
+      // Implicit im2col through the TMA: every `tile::gather4` load fetches the 128-byte channel slice of FOUR
+      // arbitrary source rows (row indices from the tap table; -1 and channels past C are zero-filled by the TMA)
+      // into 512 contiguous, 128B-swizzled bytes of the raw stage and completes on the stage's mbarrier.
+      // 64 loads per chunk, dealt round-robin to the gather warps; the LSU is not involved (a cp.async gather costs
+      // ~10 shared-memory wavefronts per instruction and made the kernel shared-memory bound).
+      // the raw stages are free at the start of a tile (every split of the previous tile has completed)
+      gather_chunk(cb, round0);
+      if (len > 1) gather_chunk(cb + 1, round0 + 1);
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
-        const int ca = cb + c;
         epoch_boundary(c);
         if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 0, c);
-        if (c == 0 || ca % gs == 0) {                               // first chunk of a group
-          const int g = ca / gs - grp_first;
-          if (g + ahead < ngroups) {
-            const uint32_t R2 = grp0 + static_cast<uint32_t>(g + ahead), st2 = R2 % nstg;
-            if (g >= 1) mbar_wait(smem_u32(&bar_raw_empty[st2]), ((R2 - nstg) / nstg) & 1, 0x30000u + round);
-            if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 1, c);
-            issue_group(g + ahead, R2);
-          }
+        if (c + 2 < len) {
+          const uint32_t r2 = round + 2, st2 = r2 % TC_A_STAGES;
+          // stage st2 was last filled for round r2-3: wait until the split warps have read it
+          if (c + 2 >= TC_A_STAGES) mbar_wait(smem_u32(&bar_raw_empty[st2]), ((r2 - TC_A_STAGES) / TC_A_STAGES) & 1, 0x30000u + round);
+          if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 1, c);
+          gather_chunk(cb + c + 2, r2);
         }
         if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 2, c);
         if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 3, c);
@@ -691,7 +605,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       }
     }
     mma_rounds = round0 + static_cast<uint32_t>(len);
-    grp_rounds = grp0 + static_cast<uint32_t>(ngroups);
     TC_TILE_TRACE(3);
 
     // ---- last epoch + epilogue (all 16 warps): bias, activation, one contiguous 256-byte store per thread
@@ -874,15 +787,6 @@ static int make_rows_map(CUtensorMap* tm, const float* x, int C, long long rows,
   return rc == CUDA_SUCCESS ? WMD_OK : WMD_ERR_UNSUPPORTED;
 }
 
-// WMD_TC_SHARE_TAPS=0 turns the shared three-tap groups off (A/B measurements); read once
-static bool tc_share_taps() {
-  static const bool on = [] {
-    const char* e = getenv("WMD_TC_SHARE_TAPS");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
-
 template <int BN>
 static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
@@ -911,7 +815,7 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN) * (splits > 0 ? splits : 1);
   const long long cap = sm_count();
   const int grid = splits == 0 ? static_cast<int>(cap) : static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
-  conv_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial, tm0, tm1, tc_share_taps() ? 1 : 0);
+  conv_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial, tm0, tm1);
   int rc = launched();
   if (rc != WMD_OK || splits == 1) return rc;
   const int nchunks = d.taps * ((d.c0 + TC_BK - 1) / TC_BK + (d.c1 + TC_BK - 1) / TC_BK);
