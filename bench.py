@@ -550,7 +550,7 @@ def run_native(args, rank, world, local_rank):
             % (e2e_ms / args.steps, e2e_h2d / 1e6, zc, zc_ms / args.steps, zc_h2d / 1e6, zc_in_place / 1e6))
         if zc_ms < e2e_ms:
             e2e_dma = {"value": round(n_global * args.steps / (e2e_ms * 1e-3), 1), "unit": UNIT,
-                       "h2d_bytes_per_step": e2e_h2d, "ms_per_step": round(e2e_ms / args.steps, 3),
+                       "h2d_bytes_per_step": e2e_h2d * world, "ms_per_step": round(e2e_ms / args.steps, 3),
                        "note": "every feature map DMA-copied whole (the plain path)"}
             e2e_ms, e2e_h2d = zc_ms, zc_h2d + zc_in_place
             e2e_note = ("pinned host features; the other maps DMA-copied one step ahead on a copy stream, skip map(s) %s read in "
@@ -665,9 +665,9 @@ def run_native(args, rank, world, local_rank):
                             "note": "same step issued launch by launch from Python (no CUDA graph)"},
             "value_channels_last": {"value": round(value_cl, 1), "unit": UNIT, "ms_per_step": round(ms_cl / args.steps, 3),
                                     "note": "same step, encoder features in torch.channels_last: used zero-copy, no layout transposes"},
-            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
-                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(e2e_ms / args.steps, 3),
-                    "note": e2e_note},
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": e2e_h2d * world,
+                    "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": round(e2e_ms / args.steps, 3),
+                    "note": e2e_note + ("; byte counts are the whole job's (rank 0's x %d ranks)" % world if world > 1 else "")},
             "e2e_dma": e2e_dma,
             "gpu_launches": int(launches_t.item()),
             "clocks": clocks,

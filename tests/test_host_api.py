@@ -79,3 +79,30 @@ def test_synthetic_generators_are_deterministic():
     sd = synth.random_state_dict({"c.weight": (4, 3, 3, 3), "c.bias": (4,)}, seed=1)
     assert abs(float(sd["c.weight"].abs().max())) <= 1 / np.sqrt(27) + 1e-7
     assert float(sd["c.weight"].double().sum()) == pytest.approx(-0.3225997, abs=1e-5)   # frozen MT19937 stream
+
+
+def test_bench_byte_accounting_matches_the_survey_formulas():
+    """bench.account(): the algorithmic bytes / flops behind `roofline.achieved`."""
+    import bench
+    n, h, w = 2, 8, 16
+    assert bench.account("idwt_haar", dict(n=n, c=1, h=h, w=w, disp=False))[0] == 32 * n * h * w
+    assert bench.account("idwt_haar", dict(n=n, c=1, h=h, w=w, disp=True))[0] == 48 * n * h * w
+    assert bench.account("nchw_to_rows", dict(n=n, c=64, hw=h * w))[0] == 8 * n * 64 * h * w
+    assert bench.account("nchw_to_rows", dict(n=n, c=64, hw=h * w, marked=10))[0] == 8 * 64 * 10 + n * h * w
+    conv = dict(n=n, h=h, w=w, taps=9, c0=32, c1=16, cout=8, shift0=1, count=None, max_rows=n * h * w, m_in0=None, m_in1=None)
+    by, fl = bench.account("conv_rows_tc", conv)
+    m = n * h * w
+    assert fl == 2 * 9 * 48 * 8 * m
+    assert by == 4 * (n * (h // 2) * (w // 2) * 32 + m * 16 + m * 8) + 4 * (9 * 48 * 8 + 8)
+    by, fl = bench.account("head_mlp", dict(c=32, n1=64, nz=54, count=None, max_rows=100))
+    assert (by, fl) == (4 * 100 * (32 + 56) + 4 * (64 * 32 + 54 * 64 + 64), 2 * 100 * (32 * 64 + 64 * 54))
+    recs = [("conv_rows_tc", 0.2, dict(conv, kind="tc")), ("idwt_haar", 0.01, dict(n=n, c=1, h=h, w=w, disp=True))] * 2
+    table = bench.conv_layer_table(recs, 6500.0, 1600.0, 2)
+    assert len(table) == 1 and table[0]["rows"] == m and table[0]["engine"] == "tcgen05_3xtf32"
+    main, per_kernel = bench.roofline_from(recs, 6500.0, 1600.0, "test", 2, 1361.0)
+    assert main["kernel"] == "conv_rows_tc" and main["bound"] == "tensor" and set(per_kernel) == {"conv_rows_tc", "idwt_haar"}
+    assert main["step_view"]["algorithmic_bytes_per_step"] == by_sum(recs, bench) // 2
+
+
+def by_sum(recs, bench):
+    return sum(bench.account(name, info)[0] for name, _, info in recs)
