@@ -334,6 +334,7 @@ def test_layout_move_options_are_bit_identical_eager_and_graphed():
     try:
         for overlap, gated in ((True, False), (False, True), (True, True)):
             mod.overlap_layout, mod.gated_layout = overlap, gated
+            mod.overlap_compaction = overlap                       # compactions on parallel streams: same kernels, same data
             for _ in range(3):                               # repeated: allocator reuse across the two streams
                 got = mod(feats, thr)
                 torch.cuda.synchronize()
@@ -366,7 +367,7 @@ def test_layout_move_options_are_bit_identical_eager_and_graphed():
         with pytest.raises(kd.WmdError):                       # without the gated move nothing reads host memory
             mod(on_host, thr)
     finally:
-        mod.overlap_layout = mod.gated_layout = False
+        mod.overlap_layout = mod.gated_layout = mod.overlap_compaction = False
 
 
 def test_fused_head_stages_match_the_two_launch_path():
@@ -394,3 +395,22 @@ def test_fused_head_stages_match_the_two_launch_path():
 def _lib_launches():
     from wavelet_monodepth_b200 import _lib
     return _lib.launch_count()
+
+
+def test_factored_ll_head_matches_the_direct_head_kernel():
+    """factored_ll: level 4 computes the LL head's 3x3 stage as nine more tap-product columns of the +/- heads' GEMM and
+    a 9-float gather-sum, instead of the warp-per-pixel head kernel.  Same arithmetic up to summation order."""
+    mod, _, feats = _full_kitti(synth.RESNET18_CH, 3, 192, 640)
+    mod.factored_ll = False
+    want = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in mod(feats, 0.05).items()}
+    mod.factored_ll = True
+    try:
+        got = mod(feats, 0.05)
+        torch.cuda.synchronize()
+    finally:
+        mod.factored_ll = False
+    assert rel_err(got[("wavelets", 3, "LL")], want[("wavelets", 3, "LL")]) <= 1e-5
+    for s in range(4):
+        assert rel_err(got[("disp", s)], want[("disp", s)]) <= 1e-5, s
+        flips = float((got[("wavelet_mask", s)] != want[("wavelet_mask", s)]).float().mean())
+        assert flips <= 1e-4, (s, flips)

@@ -55,9 +55,10 @@ def _pm(fn):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    """One side stream per device for the layout moves (created lazily, reused: CUDA graphs fork/join through it)."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+def _side_stream(device, which=0):
+    """Side streams per device (0: layout moves, 1-2: compactions), created lazily and reused: CUDA graphs fork/join
+    through them."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), which)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -151,6 +152,10 @@ class _WaveDecoderBase(nn.Module):
         self.gated_layout = os.environ.get("WMD_GATED_LAYOUT", "0") == "1"
         # run the two 1x1 head stages of the fine levels as one fused kernel (WMD_FUSED_HEADS=0/1 sets the default)
         self.fused_heads = os.environ.get("WMD_FUSED_HEADS", "1") == "1"
+        # level 4: the LL head's 3x3 stage rides in the tap-product GEMM of the +/- heads (WMD_FACTORED_LL=0/1)
+        self.factored_ll = os.environ.get("WMD_FACTORED_LL", "1") == "1"
+        # compactions of the level's three active sets on parallel streams (WMD_OVERLAP_COMPACTION=0/1)
+        self.overlap_compaction = os.environ.get("WMD_OVERLAP_COMPACTION", "1") == "1"
 
     # ---- packed parameters ------------------------------------------------------------------
     def _upconv(self, i, j):
@@ -175,9 +180,20 @@ class _WaveDecoderBase(nn.Module):
         return packed, bias, offs, run
 
     def _head_taps(self, i, offs, ctot):
-        """Factored +/- 3x3 stage: packed (54, ctot) tap-product weight and the 6 biases [+ | -]."""
+        """Factored +/- 3x3 stage: packed (54, ctot) tap-product weight and the 6 biases [+ | -].
+
+        With factored_ll, level 4 appends the LL head's nine tap filters as columns 54..62 (same 64-wide GEMM tile)."""
         cp, cn = self.convs[("waveconv", i, 1)][2].conv, self.convs[("waveconv", i, -1)][2].conv
         kind = ops.default_conv_kind()
+        if i == 4 and self.factored_ll:
+            cl = self.convs[("waveconv", i, 0)][2].conv
+            wz = self._packs.get(("headtaps+ll", i, kind), [cp.weight, cn.weight, cl.weight],
+                                 lambda: ops.pack_weight(torch.cat([
+                                     ops.head_tap_weight([cp.weight, cn.weight], [offs[1], offs[-1]], ctot),
+                                     ops.head_tap_weight([cl.weight], [offs[0]], ctot)], 0)))
+            bz = self._packs.get(("headtapsb", i), [cp.bias, cn.bias],
+                                 lambda: torch.cat([cp.bias.detach(), cn.bias.detach()]).contiguous())
+            return wz, bz
         wz = self._packs.get(("headtaps", i, kind), [cp.weight, cn.weight],
                              lambda: ops.pack_weight(ops.head_tap_weight([cp.weight, cn.weight], [offs[1], offs[-1]], ctot)))
         bz = self._packs.get(("headtapsb", i), [cp.bias, cn.bias],
@@ -254,15 +270,25 @@ class _WaveDecoderBase(nn.Module):
             if sparse:
                 if yl is None:
                     raise WmdError("a sparse level needs a previous dense level (depth_decoder.py:344)")
+                ev4 = ev5 = None
+                if self.overlap_compaction:
+                    # the three compactions are independent: S4 / S5 go to two side streams (own workspaces) and are
+                    # joined where their lists are first read (upconv(i,1) / the head scatter)
+                    (map4, pix4, off4), ev4 = ops.compact(masks["S4"], stream=_side_stream(dev, 1), ws_slot=1)
+                    (_, pix5, off5), ev5 = ops.compact(masks["S5"], want_idxmap=False, stream=_side_stream(dev, 2), ws_slot=2)
                 gmap = ops.gate_map(masks["S1"], prev_map)
                 map2, pix2, off2 = ops.compact(masks["S2"])
-                map4, pix4, off4 = ops.compact(masks["S4"])
-                _, pix5, off5 = ops.compact(masks["S5"], want_idxmap=False)
+                if not self.overlap_compaction:
+                    map4, pix4, off4 = ops.compact(masks["S4"])
+                    _, pix5, off5 = ops.compact(masks["S5"], want_idxmap=False)
                 counts[i] = (off2, off4, off5)
                 xa = ops.conv_rows(x_rows, x_c, wp0, b0, c, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, map0=gmap,
                                    pixels=pix2, count=off2[n:], m_in0=_pm(lambda: (gmap >= 0).sum()))
                 if skip_done is not None:
                     torch.cuda.current_stream(dev).wait_event(skip_done)
+                if ev4 is not None:
+                    torch.cuda.current_stream(dev).wait_event(ev4)
+                    torch.cuda.current_stream(dev).wait_event(ev5)
                 xb = ops.conv_rows(xa, c, wp1, b1, c, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_ELU, map0=map2,
                                    shift0=1, x1=skip_rows, c1=cs, gate=masks["S3"], pixels=pix4, count=off4[n:],
                                    m_in0=off2[n:], m_in1=_pm(lambda: masks["S3"].sum()))
@@ -285,7 +311,8 @@ class _WaveDecoderBase(nn.Module):
                     _, pix5, off5 = ops.compact(masks["S5"], want_idxmap=False)
                     head_kw = dict(pixels=pix5, count=off5[n:])
                 prev_map = None
-            if i == 4:
+            ll_in_gemm = i == 4 and self.factored_ll
+            if i == 4 and not ll_in_gemm:
                 wl, bl = self._head_3x3(i, 0)
                 yl = ops.head_conv3x3(t, c // 4, offs[0], wl, bl, n, 2 * h, 2 * w, 1, scale=float(2 ** i),
                                       act=ACT_SIGMOID, pad=PAD_REFLECT)
@@ -296,7 +323,10 @@ class _WaveDecoderBase(nn.Module):
             elif sparse:
                 z = ops.conv_rows(t, c1x1, wz, None, 54, n, 2 * h, 2 * w, taps=1, pixels=pix4, count=off4[n:], m_in0=off4[n:])
             else:
-                z = ops.conv_rows(t, c1x1, wz, None, 54, n, 2 * h, 2 * w, taps=1)
+                z = ops.conv_rows(t, c1x1, wz, None, 63 if ll_in_gemm else 54, n, 2 * h, 2 * w, taps=1)
+            if ll_in_gemm:
+                yl = ops.head_gather(z, 1, self.convs[("waveconv", i, 0)][2].conv.bias.detach(), n, 2 * h, 2 * w, 1,
+                                     scale=float(2 ** i), act=ACT_SIGMOID, pad=PAD_REFLECT, col0=54)
             yh = ops.head_gather(z, 6, bz, n, 2 * h, 2 * w, 3, scale=float(2 ** (i - 1)), act=ACT_SIGMOID, dual=True,
                                  pad=PAD_REFLECT, **head_kw)
             out[("wavelets", i - 1, "LL")] = yl

@@ -49,11 +49,12 @@ class _Scratch:
             self.splitk_ws[device] = buf
         return buf
 
-    def compact(self, device, nbytes):
-        buf = self.compact_ws.get(device)
+    def compact(self, device, nbytes, slot=0):
+        """slot: compactions that may run concurrently (different streams) need different workspaces."""
+        buf = self.compact_ws.get((device, slot))
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(nbytes, 1 << 16), dtype=_u8, device=device)
-            self.compact_ws[device] = buf
+            self.compact_ws[(device, slot)] = buf
         return buf
 
 
@@ -194,8 +195,12 @@ def level_masks(yh, thresh, n=None, h=None, w=None, device=None, want=("S0", "S1
     return out
 
 
-def compact(mask, want_idxmap=True, want_pixels=True):
-    """mask uint8 (N,1,H,W) or (N,H,W) -> idxmap int32 (N,H,W) | None, pixels int32 (N*H*W,) | None, offsets int32 (N+1,)."""
+def compact(mask, want_idxmap=True, want_pixels=True, stream=None, ws_slot=0):
+    """mask uint8 (N,1,H,W) or (N,H,W) -> idxmap int32 (N,H,W) | None, pixels int32 (N*H*W,) | None, offsets int32 (N+1,).
+
+    stream: optional side stream to run on (it first waits for the current stream, which produced `mask`); then returns
+    ((idxmap, pixels, offsets), event) and the consumer stream must wait for the event.  Outputs are allocated on the
+    current stream.  ws_slot: workspace to use - concurrent compactions must not share one."""
     lib = _lib.load()
     mask = _dense(mask, _u8)
     n, h, w = mask.shape[0], mask.shape[-2], mask.shape[-1]
@@ -204,12 +209,23 @@ def compact(mask, want_idxmap=True, want_pixels=True):
     pixels = torch.empty((n * h * w,), dtype=_i32, device=dev) if want_pixels else None
     offsets = torch.empty((n + 1,), dtype=_i32, device=dev)
     nbytes = lib.wmd_compact_ws_bytes(n, h, w)
-    ws = _scratch.compact(dev, nbytes)
-    with _prof('compact_mask', lambda: dict(n=n, h=h, w=w, idxmap=idxmap is not None, pixels=pixels is not None, offsets=offsets)):
-        rc = lib.wmd_compact_mask(_lib.ptr(mask), _lib.ptr(idxmap), _lib.ptr(pixels), _lib.ptr(offsets), n, h, w,
-                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
-    _lib.check(rc, "wmd_compact_mask")
-    return idxmap, pixels, offsets
+    ws = _scratch.compact(dev, nbytes, ws_slot)
+
+    def launch():
+        with _prof('compact_mask', lambda: dict(n=n, h=h, w=w, idxmap=idxmap is not None, pixels=pixels is not None, offsets=offsets)):
+            rc = lib.wmd_compact_mask(_lib.ptr(mask), _lib.ptr(idxmap), _lib.ptr(pixels), _lib.ptr(offsets), n, h, w,
+                                      _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "wmd_compact_mask")
+
+    if stream is None:
+        launch()
+        return idxmap, pixels, offsets
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(stream):
+        launch()
+        done = torch.cuda.Event()
+        done.record(stream)
+    return (idxmap, pixels, offsets), done
 
 
 def gate_map(gate, idxmap=None):
@@ -523,15 +539,19 @@ def head_tap_weight(w_list, offsets, ctot):
 
 
 def head_gather(z, groups, bias, n, h, w, cout, scale=1.0, act=ACT_NONE, dual=False, pad=PAD_REFLECT, idxmap=None,
-                pixels=None, count=None, max_rows=None, out=None):
-    """Sum the nine per-tap products of z (rows x >= 9*groups) around every output pixel -> dense (N,cout,H,W)."""
+                pixels=None, count=None, max_rows=None, out=None, col0=0):
+    """Sum the nine per-tap products of z (rows x >= 9*groups) around every output pixel -> dense (N,cout,H,W).
+
+    col0: first column of z that belongs to this head (its nine [tap][group] blocks start there)."""
     lib = _lib.load()
+    if col0 < 0 or col0 + 9 * groups > z.shape[1]:
+        raise _lib.WmdError("head_gather: columns %d..%d do not fit rows of %d" % (col0, col0 + 9 * groups, z.shape[1]))
     total = n * h * w
     max_rows = total if max_rows is None else int(max_rows)
     if out is None:
         out = (torch.zeros if pixels is not None else torch.empty)((n, cout, h, w), dtype=_f32, device=z.device)
     with _prof('head_gather', lambda: dict(n=n, h=h, w=w, groups=groups, cout=cout, count=count, max_rows=max_rows)):
-        rc = lib.wmd_head_gather_f32(_lib.ptr(z, _f32), z.shape[1], groups, _lib.ptr(idxmap, _i32), _lib.ptr(bias, _f32),
+        rc = lib.wmd_head_gather_f32(_lib.ptr(z, _f32) + 4 * col0, z.shape[1], groups, _lib.ptr(idxmap, _i32), _lib.ptr(bias, _f32),
                                      float(scale), act, int(bool(dual)), pad, _lib.ptr(pixels, _i32), _lib.ptr(count, _i32),
                                      max_rows, _lib.ptr(out, _f32), cout, n, h, w, _lib.stream_ptr())
     _lib.check(rc, "wmd_head_gather_f32")
