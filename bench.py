@@ -349,7 +349,7 @@ def cpu_frames_per_sec(wl_name, frames, budget_s=20.0, first_frame=0, batch=None
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    frames_per_step = 4
+    frames_per_step = 16                                   # ~2 s of CPU work per step on the box's host cores
     cores = cpu_pick_threads(args.workload)
     per_step_budget = max(2.0, 150.0 / max(args.steps + args.warmup, 1))     # whole run stays within a few minutes
     for w in range(args.warmup):
