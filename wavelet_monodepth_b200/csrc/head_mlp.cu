@@ -210,11 +210,14 @@ static int launch_head_mlp(const float* x, int ldx, const float* packed, float s
                            float* z, int ldz, cudaStream_t stream) {
   using Cfg = HeadMlpCfg<C, N1>;
   constexpr size_t smem = static_cast<size_t>(Cfg::PACKED) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(head_mlp_kernel<C, N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
-      return record(cudaGetLastError());
-    configured = true;
+  static bool attr_done[64] = {};                 // per device: the attribute belongs to the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    const int rc = record(cudaFuncSetAttribute(head_mlp_kernel<C, N1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem)));
+    if (rc != WMD_OK) return rc;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const int tiles = ceil_div(max_rows, 16 * HM_WARPS);
   const int grid = tiles < sm_count() ? tiles : sm_count();
