@@ -382,6 +382,25 @@ def run_reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------ native arm
+class _Guard:
+    """with _Guard(name, active, sink): a secondary section of the bench.  On one GPU an exception inside it is logged and
+    recorded in `sink` instead of costing the headline line; with several ranks it propagates (a rank that skipped the
+    section's collectives would hang the others)."""
+
+    def __init__(self, name, active, sink):
+        self.name, self.active, self.sink = name, active, sink
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is None or not self.active or not issubclass(et, Exception):
+            return False
+        log("[bench] section %s failed: %r" % (self.name, ev))
+        self.sink[self.name] = repr(ev)[:300]
+        return True
+
+
 def time_device(step_fn, steps, warmup, dist, world):
     for _ in range(warmup):
         step_fn()
@@ -412,6 +431,7 @@ def run_native(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peak_gbs, peak_tf, peak_src, peak_tf_sus = measured_peaks()
+    section_errors = {}
 
     def setup(wl_name):
         wl = WORKLOADS[wl_name]
@@ -542,12 +562,17 @@ def run_native(args, rank, world, local_rank):
         zc = tuple(int(k) for k in args.e2e_zero_copy.split(","))
         was = dec.gated_layout
         dec.gated_layout = True
+        zc_ms = None
         try:
-            zc_ms, zc_h2d, zc_in_place = run_e2e(zc)
+            with _Guard("e2e_zero_copy", world == 1, section_errors):
+                zc_ms, zc_h2d, zc_in_place = run_e2e(zc)
         finally:
             dec.gated_layout = was
-        log("[e2e] DMA %.2f ms/step (%.0f MB) ; zero-copy skips %s %.2f ms/step (%.0f MB DMA + %.0f MB in place)"
-            % (e2e_ms / args.steps, e2e_h2d / 1e6, zc, zc_ms / args.steps, zc_h2d / 1e6, zc_in_place / 1e6))
+        if zc_ms is None:                                            # the variant failed (N = 1 only): keep the DMA figure
+            zc_ms, zc_h2d, zc_in_place = float("inf"), 0, 0
+        if zc_ms != float("inf"):
+            log("[e2e] DMA %.2f ms/step (%.0f MB) ; zero-copy skips %s %.2f ms/step (%.0f MB DMA + %.0f MB in place)"
+                % (e2e_ms / args.steps, e2e_h2d / 1e6, zc, zc_ms / args.steps, zc_h2d / 1e6, zc_in_place / 1e6))
         if zc_ms < e2e_ms:
             e2e_dma = {"value": round(n_global * args.steps / (e2e_ms * 1e-3), 1), "unit": UNIT,
                        "h2d_bytes_per_step": e2e_h2d * world, "ms_per_step": round(e2e_ms / args.steps, 3),
@@ -576,56 +601,58 @@ def run_native(args, rank, world, local_rank):
     # ---- 4. secondary workload of the metric (device-resident only)
     also = None
     if args.workload == MAIN and not args.no_also:
-        del resident
-        torch.cuda.empty_cache()
-        wl2, dec2, host2 = setup(ALSO)
-        res2 = [f.to(dev) for f in host2]
-        n2 = wl2["per_gpu_batch"] * world
+        with _Guard("also", world == 1, section_errors):
+            del resident
+            torch.cuda.empty_cache()
+            wl2, dec2, host2 = setup(ALSO)
+            res2 = [f.to(dev) for f in host2]
+            n2 = wl2["per_gpu_batch"] * world
 
-        graph2 = graphs.GraphedSparseDecoder(dec2, res2, THRESH) if use_graph else None
+            graph2 = graphs.GraphedSparseDecoder(dec2, res2, THRESH) if use_graph else None
 
-        def step2():
-            o = graph2.replay() if use_graph else dec2(res2, THRESH)
-            if world > 1:
-                shard.all_gather_batch(o[("disp", 0)], n2)
-            last["out2"] = o
+            def step2():
+                o = graph2.replay() if use_graph else dec2(res2, THRESH)
+                if world > 1:
+                    shard.all_gather_batch(o[("disp", 0)], n2)
+                last["out2"] = o
 
-        ms2 = time_device(step2, args.steps, max(args.warmup, 3), dist, world)
-        o2 = last["out2"]
-        also = {"workload": ALSO, "value": round(n2 * args.steps / (ms2 * 1e-3), 1), "unit": UNIT,
-                "ms_per_step": round(ms2 / args.steps, 3), "global_batch": n2,
-                "wavelet_mask_density": {str(s): round(float(o2[("wavelet_mask", s)].float().mean()), 4) for s in (3, 2, 1, 0)},
-                "total_ops_per_frame": o2["total_ops"] / wl2["per_gpu_batch"]}
+            ms2 = time_device(step2, args.steps, max(args.warmup, 3), dist, world)
+            o2 = last["out2"]
+            also = {"workload": ALSO, "value": round(n2 * args.steps / (ms2 * 1e-3), 1), "unit": UNIT,
+                    "ms_per_step": round(ms2 / args.steps, 3), "global_batch": n2,
+                    "wavelet_mask_density": {str(s): round(float(o2[("wavelet_mask", s)].float().mean()), 4) for s in (3, 2, 1, 0)},
+                    "total_ops_per_frame": o2["total_ops"] / wl2["per_gpu_batch"]}
 
     # ---- 4b. NYUv2 workload of configs[3]: DenseNet161 pyramid 640x480, 8 frames/GPU, SparseDecoderWave thr 0.1
     also_nyu = None
     if args.workload == MAIN and not args.no_also:
-        from wavelet_monodepth_b200 import nyu_decoders
-        torch.cuda.empty_cache()
-        nmod = nyu_decoders.SparseDecoderWave(enc_features=list(NYU["ch"]), decoder_width=0.5)
-        synth.load_random(nmod, seed=NYU["param_seed"], gains={k: SYNTH["head_gain"] for k in NYU["heads"]},
-                          highpass=NYU["heads"])
-        nmod = nmod.to(dev).eval()
-        nb = NYU["per_gpu_batch"]
-        nfeats = [f.to(dev) for f in synth.blocky_features(
-            synth.nyu_feature_shapes(nb, NYU["height"], NYU["width"], NYU["ch"]), seed=NYU["feat_seed"] + rank * nb,
-            cell=SYNTH["cell"], texture=SYNTH["texture"])]
-        n3 = nb * world
+        with _Guard("also_nyu", world == 1, section_errors):
+            from wavelet_monodepth_b200 import nyu_decoders
+            torch.cuda.empty_cache()
+            nmod = nyu_decoders.SparseDecoderWave(enc_features=list(NYU["ch"]), decoder_width=0.5)
+            synth.load_random(nmod, seed=NYU["param_seed"], gains={k: SYNTH["head_gain"] for k in NYU["heads"]},
+                              highpass=NYU["heads"])
+            nmod = nmod.to(dev).eval()
+            nb = NYU["per_gpu_batch"]
+            nfeats = [f.to(dev) for f in synth.blocky_features(
+                synth.nyu_feature_shapes(nb, NYU["height"], NYU["width"], NYU["ch"]), seed=NYU["feat_seed"] + rank * nb,
+                cell=SYNTH["cell"], texture=SYNTH["texture"])]
+            n3 = nb * world
 
-        def step3():
-            o = nmod(nfeats, NYU["thresh"])
-            if world > 1:
-                shard.all_gather_batch(o[("disp", 0)], n3)
-            last["out3"] = o
+            def step3():
+                o = nmod(nfeats, NYU["thresh"])
+                if world > 1:
+                    shard.all_gather_batch(o[("disp", 0)], n3)
+                last["out3"] = o
 
-        ms3 = time_device(step3, args.steps, max(args.warmup, 3), dist, world)
-        o3 = last["out3"]
-        also_nyu = {"workload": NYU["name"], "value": round(n3 * args.steps / (ms3 * 1e-3), 1), "unit": UNIT,
-                    "ms_per_step": round(ms3 / args.steps, 3), "global_batch": n3, "thresh_ratio": NYU["thresh"],
-                    "launch_mode": "eager", "decoder": "SparseDecoderWave (NYUv2/networks/decoders/densedepth_decoder.py:224-409), batched",
-                    "wavelet_mask_density": {str(s_): round(float(o3[("wavelet_mask", s_)].float().mean()), 4) for s_ in (2, 1, 0)},
-                    "total_ops_per_frame": o3["total_ops"] / nb, "dense_total_ops_per_frame": 33463546800}
-        del nmod, nfeats
+            ms3 = time_device(step3, args.steps, max(args.warmup, 3), dist, world)
+            o3 = last["out3"]
+            also_nyu = {"workload": NYU["name"], "value": round(n3 * args.steps / (ms3 * 1e-3), 1), "unit": UNIT,
+                        "ms_per_step": round(ms3 / args.steps, 3), "global_batch": n3, "thresh_ratio": NYU["thresh"],
+                        "launch_mode": "eager", "decoder": "SparseDecoderWave (NYUv2/networks/decoders/densedepth_decoder.py:224-409), batched",
+                        "wavelet_mask_density": {str(s_): round(float(o3[("wavelet_mask", s_)].float().mean()), 4) for s_ in (2, 1, 0)},
+                        "total_ops_per_frame": o3["total_ops"] / nb, "dense_total_ops_per_frame": 33463546800}
+            del nmod, nfeats
 
     # ---- 5. CPU baseline (rank 0, N == 1 only)
     cpu = None
@@ -677,6 +704,7 @@ def run_native(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "also": also,
             "also_nyu": also_nyu,
+            "section_errors": section_errors or None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
