@@ -287,6 +287,42 @@ def pin_known_answers(save):
         json.dump(kat, f, indent=1, sort_keys=True)
 
 
+def pin_full_size(only_check=True):
+    """BASELINE configs[0]/[1] size (ResNet18 pyramid, 640x192, one frame) with the bench's synthetic weights / features:
+    the restatement against the reference's dense decoder and its sparse decoder at thr 0 and 0.05.  Nothing is stored
+    except a small summary (op counts, mask pixel counts, plane checksums) - the point is that the pin also holds at a
+    full-size configuration with non-degenerate masks, not only on the tiny fixtures."""
+    import bench
+    _, dec = import_reference("KITTI")
+    ch = synth.RESNET18_CH
+    ref_dense = dec.DepthWaveProgressiveDecoder(np.array(ch)).eval()
+    ref_sparse = dec.SparseDepthWaveProgressiveDecoder(np.array(ch)).eval()
+    sd = synth.random_state_dict(synth.module_shapes(ref_dense), seed=bench.SYNTH["param_seed"],
+                                 gains={k: bench.SYNTH["head_gain"] for k in bench.HEAD_KEYS}, highpass=bench.HEAD_KEYS)
+    ref_dense.load_state_dict(sd, strict=False)
+    ref_sparse.load_state_dict(sd, strict=False)
+    feats = synth.blocky_features(synth.kitti_feature_shapes(1, 192, 640, ch), seed=bench.SYNTH["feat_seed"],
+                                  cell=bench.SYNTH["cell"], texture=bench.SYNTH["texture"])
+    summary = {}
+    with torch.no_grad():
+        compare(ref_dense(feats), okitti.dense_forward(sd, feats), "KITTI R18 640x192 dense decoder (full size)")
+        for thr in (0.0, 0.05):
+            r = silence(ref_sparse, feats, thr)
+            o = okitti.sparse_forward(sd, feats, thr)
+            compare(r, o, "KITTI R18 640x192 sparse thr=%g (full size)" % thr)
+            summary["thr%g" % thr] = {
+                "total_ops": int(r["total_ops"]),
+                "wavelet_mask_pixels": [int(r[("wavelet_mask", s)].sum()) for s in range(4)],
+                "disp_sum": [float(r[("disp", s)].double().sum()) for s in range(4)],
+                "disp_sumsq": [float((r[("disp", s)].double() ** 2).sum()) for s in range(4)]}
+            print("      wavelet_mask density scales 3..0:", [round(density(r, "wavelet_mask", s), 3) for s in (3, 2, 1, 0)],
+                  " total_ops", r["total_ops"])
+    with open(os.path.join(GOLDEN, "kitti_r18_640x192_summary.json"), "w") as f:
+        json.dump({"config": "ResNet18 pyramid 640x192, 1 frame, bench.py synthetic weights/features (param_seed %d, "
+                             "feat_seed %d)" % (bench.SYNTH["param_seed"], bench.SYNTH["feat_seed"]),
+                   "reference_outputs": summary}, f, indent=1, sort_keys=True)
+
+
 def pin_state_dicts():
     """Record the reference modules' state-dict keys/shapes: the checkpoint-compatibility contract."""
     rec = {}
@@ -323,6 +359,7 @@ def main():
     pin_state_dicts()
     if not args.skip_kat:
         pin_known_answers(save)
+        pin_full_size()
     print("golden vectors written to", GOLDEN)
 
 
