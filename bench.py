@@ -43,8 +43,8 @@ NYU = dict(name="nyu_d161_640x480_bs8", ch=synth.DENSENET161_CH, height=480, wid
            heads=["wave1.conv.", "wave2.conv.", "wave3.conv."], param_seed=11, feat_seed=2000)   # configs[3]
 MAIN = "kitti_r50_1024x320_bs32"
 ALSO = "kitti_r18_640x192_bs16"
-HEAD_KEYS = ["decoder.%d.2.conv." % k for k in (3, 4, 7, 8, 11, 12, 15, 16)]   # +/- coefficient heads' 3x3 stage
-SYNTH = dict(param_seed=7, feat_seed=1000, cell=16, texture=0.01, head_gain=4.0)
+HEAD_KEYS = synth.KITTI_HEAD_KEYS                                                # +/- coefficient heads' 3x3 stage
+SYNTH = synth.BENCH_SYNTH
 THRESH = 0.05
 METRIC, UNIT = "decoder_frames_per_sec", "frames/s"
 FP32_SIMT_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop x max SM clock
@@ -55,14 +55,11 @@ def log(*a):
 
 
 def synth_params(module):
-    return synth.load_random(module, seed=SYNTH["param_seed"], gains={k: SYNTH["head_gain"] for k in HEAD_KEYS},
-                             highpass=HEAD_KEYS)
+    return synth.bench_kitti_params(module)
 
 
 def synth_features(wl, n, first_sample, pin):
-    shapes = synth.kitti_feature_shapes(n, wl["height"], wl["width"], wl["ch"])
-    return synth.blocky_features(shapes, seed=SYNTH["feat_seed"] + first_sample, cell=SYNTH["cell"],
-                                 texture=SYNTH["texture"], pin=pin)
+    return synth.bench_kitti_features(n, wl["height"], wl["width"], wl["ch"], first_sample, pin)
 
 
 def measured_peaks():
@@ -187,8 +184,10 @@ def account(name, info):
     return 0, 0
 
 
-def conv_layer_table(records, peak_gbs, peak_tf, steps):
-    """One line per gather-GEMM launch of a step (mean over the profiled steps): shape, active rows, time, rates."""
+def conv_layer_table(records, peak_gbs, tf32_peak, steps):
+    """One line per gather-GEMM launch of a step (mean over the profiled steps): shape, active rows, time, rates.
+    tensor_frac = algorithmic (fp32-equivalent) flops / tf32 peak; tensor_frac_executed counts the three tf32 MMAs
+    each fp32 product costs."""
     convs = [(name, ms, info) for name, ms, info in records if name in ("conv_rows", "conv_rows_tc")]
     per_step = len(convs) // max(steps, 1)
     if per_step == 0 or per_step * steps != len(convs):
@@ -206,14 +205,22 @@ def conv_layer_table(records, peak_gbs, peak_tf, steps):
                 "rows": rows, "us": round(1e3 * ms, 1), "fp32_eq_tflops": round(tf, 1),
                 "hbm_frac": round(by / (ms * 1e-3) / 1e9 / peak_gbs, 3) if ms > 0 else 0.0}
         if name == "conv_rows_tc":
-            line["tensor_frac"] = round(3.0 * tf / (peak_tf / 2.0), 3)
+            line["tensor_frac"] = round(tf / tf32_peak, 3)
+            line["tensor_frac_executed"] = round(3.0 * tf / tf32_peak, 3)
         else:
             line["fma_frac"] = round(tf / FP32_SIMT_PEAK_TFLOPS, 3)
         table.append(line)
     return table
 
 
-def roofline_from(records, peak_gbs, peak_tf, peak_src, steps, peak_tf_sustained=None):
+def roofline_from(records, peak_gbs, peak_tf, peak_src, steps, peak_tf_sustained=None, tf32_peak=None):
+    """roofline object of the dominant kernel + per-kernel table.
+
+    Tensor-bound kernel: `achieved` = ALGORITHMIC flops (2 * taps * Cin * Cout * M_out) / CUDA-event time and
+    `frac` = achieved / tf32 peak.  The kernel executes three tf32 MMAs per fp32 product (3xTF32, needed for the 1e-4 /
+    exact-mask parity bar): `frac_executed_3xtf32` = 3 * achieved / peak is the fraction of the tensor pipe it keeps busy.
+    tf32 peak: measured in this process (cuBLAS TF32 GEMM 8192^3, best of 10); MEASURED_PEAKS.json's bf16 figure / 2 is
+    listed beside it."""
     agg = {}
     for name, ms, info in records:
         by, fl = account(name, info)
@@ -232,23 +239,25 @@ def roofline_from(records, peak_gbs, peak_tf, peak_src, steps, peak_tf_sustained
         }
     dom = max(agg, key=lambda k: agg[k]["ms"])
     hbm_view = dict(out[dom])
+    tf32 = tf32_peak if tf32_peak else peak_tf / 2.0
     if dom == "conv_rows_tc":
-        # tensor-bound: 3xTF32 executes 3 tf32 MMA flops per fp32-equivalent flop; tf32 dense peak = half the measured
-        # bf16 dense peak (same tcgen05 pipe, K=8 instead of K=16 per instruction)
-        tf32_peak = peak_tf / 2.0
-        executed = 3.0 * hbm_view["tflops"]
-        main = {"bound": "tensor", "achieved": round(executed, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
-                "frac": round(executed / tf32_peak, 4), "traffic": None, "kernel": dom,
-                "fp32_equivalent_tflops": hbm_view["tflops"], "avg_launch_us": hbm_view["avg_launch_us"],
+        alg = hbm_view["tflops"]
+        main = {"bound": "tensor", "achieved": round(alg, 1), "peak": round(tf32, 1), "unit": "TFLOP/s",
+                "frac": round(alg / tf32, 4), "traffic": None, "kernel": dom,
+                "frac_executed_3xtf32": round(3.0 * alg / tf32, 4),
+                "executed_tf32_tflops": round(3.0 * alg, 1),
+                "avg_launch_us": hbm_view["avg_launch_us"],
                 "launches_per_step": hbm_view["launches_per_step"], "share_of_kernel_time": hbm_view["share_of_kernel_time"],
                 "bytes_per_launch": hbm_view["bytes_per_launch"],
                 "hbm_view": {"achieved_gbs": hbm_view["achieved"], "peak_gbs": peak_gbs, "frac": hbm_view["frac"]},
-                "frac_of_sustained_peak": round(executed / (peak_tf_sustained / 2.0), 4) if peak_tf_sustained else None,
-                "peak_source": peak_src + ": burst bf16_tflops / 2 for tf32 (each launch is timed alone between two "
-                               "events; frac_of_sustained_peak uses bf16_tflops_sustained / 2)",
-                "note": "tcgen05.mma.kind::tf32, 3 MMAs per fp32 product (hi*hi + hi*lo + lo*hi), fp32 accumulation in "
-                        "TMEM; A gathered by TMA gather4 and moved to TMEM by split warps; the N=128 layers run at "
-                        "~0.8 of this peak, the N<=64 layers are bound by the gather (L2->SM path), see DESIGN.md 4"}
+                "peak_alternatives": {"tf32_measured_here_tflops": round(tf32_peak, 1) if tf32_peak else None,
+                                      "bf16_burst_over_2": round(peak_tf / 2.0, 1),
+                                      "bf16_sustained_over_2": round(peak_tf_sustained / 2.0, 1) if peak_tf_sustained else None},
+                "peak_source": ("measured in this run: cuBLAS TF32 GEMM 8192^3, best of 10 (burst; each launch is timed alone "
+                                "between two events)" if tf32_peak else peak_src + ": bf16_tflops / 2"),
+                "note": "achieved = algorithmic fp32-equivalent flops (2*taps*Cin*Cout*M_out) / event time. tcgen05.mma.kind::tf32, "
+                        "3 MMAs per fp32 product (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM drained every 1024 of K; "
+                        "per-layer figures in conv_layers, DESIGN.md 4"}
     else:
         main = dict(hbm_view)
         main.update(kernel=dom, peak_source=peak_src,
@@ -257,7 +266,11 @@ def roofline_from(records, peak_gbs, peak_tf, peak_src, steps, peak_tf_sustained
     traffic_file = os.path.join(REPO, "profiles", "ncu_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            main["traffic"] = json.load(open(traffic_file)).get(dom)
+            tr = json.load(open(traffic_file))
+            main["traffic"] = tr.get(dom)
+            for name in out:
+                if tr.get(name) is not None:
+                    out[name]["traffic"] = tr[name]
         except Exception:
             pass
     # whole step against the HBM roof (north_star: "fraction of the HBM roofline" for the fused decoder): the summed
@@ -265,14 +278,22 @@ def roofline_from(records, peak_gbs, peak_tf, peak_src, steps, peak_tf_sustained
     step_bytes = sum(a["bytes"] for a in agg.values()) / max(steps, 1)
     step_flops = sum(a["flops"] for a in agg.values()) / max(steps, 1)
     step_ms = total_ms / max(steps, 1)
+    main["hbm_frac_step"] = round(step_bytes / (step_ms * 1e-3) / 1e9 / peak_gbs, 4)
+    main["hbm_gbs_step"] = round(step_bytes / (step_ms * 1e-3) / 1e9, 1)
+    for key, kname in (("idwt", "idwt_haar"), ("idwt_fused", "head_idwt")):
+        if kname in out:
+            main[key] = {"kernel": kname, "achieved_gbs": out[kname]["achieved"], "peak_gbs": peak_gbs, "frac": out[kname]["frac"],
+                         "avg_launch_us": out[kname]["avg_launch_us"], "launches_per_step": out[kname]["launches_per_step"],
+                         "traffic": out[kname]["traffic"]}
     main["step_view"] = {"algorithmic_bytes_per_step": int(step_bytes), "kernel_ms_per_step": round(step_ms, 3),
                          "hbm_gbs": round(step_bytes / (step_ms * 1e-3) / 1e9, 1),
                          "hbm_frac": round(step_bytes / (step_ms * 1e-3) / 1e9 / peak_gbs, 4),
                          "fp32_eq_tflops": round(step_flops / (step_ms * 1e-3) / 1e12, 1),
                          "hbm_floor_ms": round(step_bytes / (peak_gbs * 1e9) * 1e3, 3),
-                         "tf32x3_floor_ms": round(3.0 * step_flops / (peak_tf / 2.0 * 1e12) * 1e3, 3),
-                         "note": "the decoder is tensor-bound, not HBM-bound, at fp32-faithful precision: 3 tf32 MMAs per "
-                                 "product put the tensor-pipe floor above the HBM floor (both listed)"}
+                         "tf32x3_floor_ms": round(3.0 * step_flops / (tf32 * 1e12) * 1e3, 3),
+                         "note": "north_star target '>= 60 % of the HBM roofline on the fused decoder' presumes an HBM-bound "
+                                 "decoder; at fp32-faithful precision (3 tf32 MMAs per product) the tensor-pipe floor is above "
+                                 "the HBM floor (both listed), so hbm_frac_step cannot reach 0.6 with exact masks"}
     return main, out
 
 
@@ -295,7 +316,7 @@ def _cpu_setup(wl_name):
     return wl, _CPU_PARAMS[wl_name]
 
 
-def _cpu_frame(wl, sd, f, batch=None):
+def _cpu_frame(wl, sd, f, batch=None, on_frame=None):
     from oracle import kitti as okitti                     # allowed here: cpu_baseline / --impl reference legs only
     b = f % wl["per_gpu_batch"]
     if batch is not None:                                  # frame b of the step's own (host) feature batch
@@ -304,8 +325,19 @@ def _cpu_frame(wl, sd, f, batch=None):
         feats = synth_features(wl, 1, b, pin=False)
     t0 = time.perf_counter()
     with torch.no_grad():
-        okitti.sparse_forward(sd, feats, THRESH)
-    return time.perf_counter() - t0
+        ref = okitti.sparse_forward(sd, feats, THRESH)
+    dt = time.perf_counter() - t0
+    if on_frame is not None:                               # parity block: outside the timed span
+        on_frame(b, ref)
+    return dt
+
+
+def _cpu_oracle_frame(wl_name, feats, thresh):
+    """Oracle outputs of one frame at `thresh` (threshold sweep's op-count / parity check)."""
+    from oracle import kitti as okitti
+    _, sd = _cpu_setup(wl_name)
+    with torch.no_grad():
+        return okitti.sparse_forward(sd, [t.contiguous() for t in feats], thresh)
 
 
 def cpu_pick_threads(wl_name):
@@ -332,7 +364,7 @@ def cpu_pick_threads(wl_name):
     return best
 
 
-def cpu_frames_per_sec(wl_name, frames, budget_s=20.0, first_frame=0, batch=None):
+def cpu_frames_per_sec(wl_name, frames, budget_s=20.0, first_frame=0, batch=None, on_frame=None):
     """Times oracle.kitti.sparse_forward (the reference's batch-1 sparse path, restated) on the host cores:
     up to `frames` frames, stopping early once `budget_s` seconds of CPU work are spent.  `batch`: host feature
     tensors to take the frames from (the GPU arm's own step inputs); otherwise frames are generated one by one."""
@@ -340,15 +372,35 @@ def cpu_frames_per_sec(wl_name, frames, budget_s=20.0, first_frame=0, batch=None
     torch.set_num_threads(cpu_pick_threads(wl_name))
     times = []
     for f in range(frames):
-        times.append(_cpu_frame(wl, sd, first_frame + f, batch))
+        times.append(_cpu_frame(wl, sd, first_frame + f, batch, on_frame))
         if sum(times) >= budget_s:
             break
     return len(times) / sum(times), times
 
 
+def workload_config(wl_name, world, thresh=None):
+    """Static description of the measured workload: identical in the native and the reference arm (the driver compares
+    the two arms' `config`).  Anything measured (mask densities, op counts) or arm-specific goes elsewhere."""
+    wl = WORKLOADS[wl_name]
+    return {
+        "workload": wl_name, "global_batch": wl["per_gpu_batch"] * world, "per_gpu_batch": wl["per_gpu_batch"],
+        "encoder": "%s pyramid %s" % ("ResNet50" if wl["ch"] == synth.RESNET50_CH else "ResNet18", list(wl["ch"])),
+        "resolution": "%dx%d" % (wl["width"], wl["height"]),
+        "thresh_ratio": THRESH if thresh is None else thresh,
+        "decoder": "SparseDepthWaveProgressiveDecoder (levels 3,2,1 sparse)",
+        "parallelism": "dp%d batch-sharded, one all-gather of disp0" % world,
+        "l2": "inputs larger than L2: %.2f GB of features read per step per GPU"
+              % (sum(4 * c * (wl["height"] // (2 << k)) * (wl["width"] // (2 << k)) for k, c in enumerate(wl["ch"]))
+                 * wl["per_gpu_batch"] / 1e9),
+        "weights": "seeded random init, high-pass coefficient heads x%.0f (synth.py)" % SYNTH["head_gain"],
+        "features": "seeded blocky maps, cell %d px, texture %.2f" % (SYNTH["cell"], SYNTH["texture"]),
+    }
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     frames_per_step = 16                                   # ~2 s of CPU work per step on the box's host cores
     cores = cpu_pick_threads(args.workload)
     per_step_budget = max(2.0, 150.0 / max(args.steps + args.warmup, 1))     # whole run stays within a few minutes
@@ -367,10 +419,12 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * spent / args.steps, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "thresh_ratio": THRESH, "frames_per_step": round(done / args.steps, 2),
-                   "note": "reference is Python/PyTorch and cannot travel to the GPU box; this arm times the oracle's "
-                           "torch-CPU port of its batch-1 sparse decoder (pinned bit-exact against the reference, "
-                           "oracle/pin_against_reference.py) on the host cores", "wall_s": round(wall, 1)},
+        "config": workload_config(args.workload, world),
+        "arm": {"frames_per_step": round(done / args.steps, 2), "wall_s": round(wall, 1),
+                "note": "the reference is Python/PyTorch and cannot travel to the GPU box; this arm times the oracle's "
+                        "torch-CPU port of its batch-1 sparse decoder (pinned bit-exact against the reference, "
+                        "oracle/pin_against_reference.py; measured ~1.4x FASTER than the reference's own code in the "
+                        "build container) on the host cores; each step is a bounded sample of the workload's frames"},
         "cpu_baseline": {"value": round(fps, 3), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d frames in %d steps of %s, one frame at a time (reference asserts batch 1); "
                                    "intra-op threads chosen by probe out of %d usable cores"
@@ -401,9 +455,14 @@ class _Guard:
         return True
 
 
-def time_device(step_fn, steps, warmup, dist, world):
+def time_device(step_fn, steps, warmup, dist, world, flush=None):
+    """`steps` calls of step_fn between two CUDA events, barrier + synchronize on both sides, max over ranks.
+    flush: called after the last step INSIDE the timed region (drains whatever the steps left in flight: the last
+    step's op-count future and all-gather)."""
     for _ in range(warmup):
         step_fn()
+    if flush:
+        flush()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -411,6 +470,8 @@ def time_device(step_fn, steps, warmup, dist, world):
     e0.record()
     for _ in range(steps):
         step_fn()
+    if flush:
+        flush()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -419,6 +480,61 @@ def time_device(step_fn, steps, warmup, dist, world):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item())
+
+
+def measure_tf32_peak(dev):
+    """Dense TF32 tensor-core throughput of this GPU, measured the way MEASURED_PEAKS.json measures bf16: cuBLAS GEMM
+    8192^3 (fp32 operands, allow_tf32), best of 10, CUDA events."""
+    was = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b)
+        best = None
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            best = t if best is None or t < best else best
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = was
+
+
+class _Stepper:
+    """One bench step = decoder replay (no host wait) + the rank's all-gather started asynchronously; the previous
+    step's op count and gathered tensor are consumed while this one runs.  flush() drains the tail."""
+
+    def __init__(self, run, gather, last):
+        self.run, self.gather, self.last, self.pending = run, gather, last, []
+
+    def _finish(self, item):
+        fut, handle, out = item
+        self.last["total_ops"] = fut.result()["total_ops"] if fut is not None else None
+        self.last["ops_result"] = fut.result() if fut is not None else None
+        if handle is not None:
+            self.last["gathered"] = handle.wait()
+        self.last["out"] = out
+
+    def step(self):
+        out = self.run()
+        fut = out.get("total_ops")
+        handle = self.gather.start(out[("disp", 0)]) if self.gather is not None else None
+        self.pending.append((fut, handle, out))
+        while len(self.pending) > 1:
+            self._finish(self.pending.pop(0))
+
+    def flush(self):
+        while self.pending:
+            self._finish(self.pending.pop(0))
 
 
 def run_native(args, rank, world, local_rank):
@@ -431,6 +547,7 @@ def run_native(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peak_gbs, peak_tf, peak_src, peak_tf_sus = measured_peaks()
+    tf32_peak = measure_tf32_peak(dev)
     section_errors = {}
 
     def setup(wl_name):
@@ -439,6 +556,7 @@ def run_native(args, rank, world, local_rank):
         dec = SparseDepthWaveProgressiveDecoder(np.array(wl["ch"]))
         synth_params(dec)
         dec = dec.to(dev).eval()
+        dec.count_ops = "async"            # total_ops via OpsFuture: the step never blocks the host (opsfuture.py)
         t0 = time.time()
         host = synth_features(wl, n_local, rank * n_local, pin=True)
         log("[rank %d] %s: synthetic features for %d frames in %.1fs" % (rank, wl_name, n_local, time.time() - t0))
@@ -448,25 +566,14 @@ def run_native(args, rank, world, local_rank):
     n_local, n_global = wl["per_gpu_batch"], wl["per_gpu_batch"] * world
     resident = [f.to(dev) for f in host]
     last = {}
+    gather = shard.OverlappedGather(n_global) if world > 1 else None
 
-    def step_eager():
-        out = dec(resident, THRESH)
-        if world > 1:
-            last["gathered"] = shard.all_gather_batch(out[("disp", 0)], n_global)
-        last["out"] = out
-
-    # serving mode: the ~70 launches of one forward captured once in a CUDA graph bound to the resident feature tensors
+    # serving mode: the launches of one forward captured once in a CUDA graph bound to the resident feature tensors
     # (graphs.py); replay = the same kernels without the per-launch host cost.  --no-graph times the eager calls instead.
     use_graph = not args.no_graph
     graph = graphs.GraphedSparseDecoder(dec, resident, THRESH) if use_graph else None
-
-    def step():
-        if not use_graph:
-            return step_eager()
-        out = graph.replay()                                        # incl. the total_ops count read-back
-        if world > 1:
-            last["gathered"] = shard.all_gather_batch(out[("disp", 0)], n_global)
-        last["out"] = out
+    eager = _Stepper(lambda: dec(resident, THRESH), gather, last)
+    main = _Stepper(graph.replay, gather, last) if use_graph else eager
 
     # ---- 1. device-resident throughput
     # clocks are sampled from before the warm-up to the end of the end-to-end pass: the two timed regions are only
@@ -475,35 +582,78 @@ def run_native(args, rank, world, local_rank):
     if sampler:
         sampler.start()
     for _ in range(max(args.warmup - 1, 0)):
-        step()
+        main.step()
+    main.flush()
     l0 = _lib.launch_count()
-    ms = time_device(step, args.steps, 1 if args.warmup else 0, dist, world)
+    ms = time_device(main.step, args.steps, 1 if args.warmup else 0, dist, world, flush=main.flush)
     launches = _lib.launch_count() - l0
     launches -= (1 if args.warmup else 0) * (launches // (args.steps + (1 if args.warmup else 0)))
     if use_graph:
         launches = graph.launches * args.steps                       # kernel nodes replayed inside the timed region
-    ms_eager = time_device(step_eager, args.steps, 1, dist, world) if use_graph else ms
+    ms_eager = time_device(eager.step, args.steps, 1, dist, world, flush=eager.flush) if use_graph else ms
     value_eager = n_global * args.steps / (ms_eager * 1e-3)
     out = last["out"]
     dens = {s: round(float(out[("wavelet_mask", s)].float().mean()), 4) for s in (3, 2, 1, 0)}
-    ops_per_frame = out["total_ops"] / n_local
+    ops_per_frame = last["total_ops"] / n_local
     value = n_global * args.steps / (ms * 1e-3)
+    # the step's outputs, kept on the host for the parity block of the cpu_baseline leg
+    out_host = {k: v.cpu() for k, v in out.items() if torch.is_tensor(v)} if (rank == 0 and world == 1 and not args.no_cpu) else None
+    if out_host is not None:
+        out_host["total_ops_per_sample"] = last["ops_result"].get("total_ops_per_sample", [last["total_ops"]])
+
+    # the collective alone (N > 1): K all-gathers of disp0 back to back, nothing else on the GPU
+    allgather_ms = None
+    if world > 1:
+        solo = shard.OverlappedGather(n_global)
+        src = out[("disp", 0)]
+        hs = []
+
+        def ag_step():
+            hs.append(solo.start(src))
+            if len(hs) > 1:
+                hs.pop(0).wait()
+
+        allgather_ms = time_device(ag_step, args.steps, 2, dist, world, flush=lambda: [h.wait() for h in hs] and hs.clear()) / args.steps
 
     # ---- 1b. same step with the features handed over channels_last (what a channels_last cuDNN encoder leaves):
     # the decoder then uses them in place and the five NCHW->rows transposes disappear
     resident_cl = [f.contiguous(memory_format=torch.channels_last) for f in resident]
-
     graph_cl = graphs.GraphedSparseDecoder(dec, resident_cl, THRESH) if use_graph else None
-
-    def step_cl():
-        o = graph_cl.replay() if use_graph else dec(resident_cl, THRESH)
-        if world > 1:
-            shard.all_gather_batch(o[("disp", 0)], n_global)
-
-    ms_cl = time_device(step_cl, args.steps, 2, dist, world)
+    cl = _Stepper(graph_cl.replay if use_graph else (lambda: dec(resident_cl, THRESH)), gather, {})
+    ms_cl = time_device(cl.step, args.steps, 2, dist, world, flush=cl.flush)
     value_cl = n_global * args.steps / (ms_cl * 1e-3)
-    del graph_cl, resident_cl
+    del graph_cl, resident_cl, cl
     torch.cuda.empty_cache()
+
+    # ---- 1c. threshold sweep (BASELINE.json configs[2]: {0, 0.02, 0.05, 0.1} on one GPU; configs[4]: {0.05, 0.1} sharded)
+    sweep = None
+    if args.workload == MAIN and not args.no_sweep:
+        sweep = []
+        thr_list = (0.0, 0.02, 0.05, 0.1) if world == 1 else (0.05, 0.1)
+        for thr in thr_list:
+            with _Guard("sweep_%g" % thr, world == 1, section_errors):
+                g = graphs.GraphedSparseDecoder(dec, resident, thr) if use_graph else None
+                lst = {}
+                st = _Stepper(g.replay if use_graph else (lambda thr=thr: dec(resident, thr)), gather, lst)
+                ms_t = time_device(st.step, args.steps, 2, dist, world, flush=st.flush)
+                o = lst["out"]
+                entry = {"thresh_ratio": thr, "value": round(n_global * args.steps / (ms_t * 1e-3), 1), "unit": UNIT,
+                         "ms_per_step": round(ms_t / args.steps, 3),
+                         "wavelet_mask_density": {str(s_): round(float(o[("wavelet_mask", s_)].float().mean()), 4) for s_ in (3, 2, 1, 0)},
+                         "total_ops_per_frame": lst["total_ops"] / n_local,
+                         "frac_of_dense_ops": round(lst["total_ops"] / n_local / 17473692295, 4)}
+                if rank == 0 and world == 1 and not args.no_cpu:
+                    # frame 0 of the step against the oracle (the reference's counter and outputs for that frame)
+                    from oracle import parity
+                    ref0 = _cpu_oracle_frame(args.workload, [t[0:1] for t in host], thr)
+                    got0 = parity.sample_of({**{k: v for k, v in o.items() if torch.is_tensor(v)},
+                                             "total_ops_per_sample": lst["ops_result"]["total_ops_per_sample"]}, 0)
+                    rep = parity.compare_kitti_sample(got0, ref0, thr)
+                    entry["oracle_check_frame0"] = {"total_ops_equal": rep["total_ops_equal"], "max_rel_err": float("%.3e" % rep["max_rel_err"]),
+                                                    "mask_hamming": sum(rep["mask_hamming"].values()), "failures": rep["failures"][:3]}
+                sweep.append(entry)
+                del g, st
+                torch.cuda.empty_cache()
 
     # ---- 2. end to end: host features -> H2D (copy stream, double buffered) -> decode -> D2H of disp0
     # zero_copy = indices of skip maps that stay in pinned host memory and are read in place by the gated layout move
@@ -519,6 +669,7 @@ def run_native(args, rank, world, local_rank):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         state = {"i": 0}
         graphs_e2e = [graphs.GraphedSparseDecoder(dec, b, THRESH) for b in bufs] if use_graph else None
+        lst = {}
 
         def enqueue_copy(slot):
             with torch.cuda.stream(copy_stream):
@@ -526,57 +677,62 @@ def run_native(args, rank, world, local_rank):
                     bufs[slot][k].copy_(host[k], non_blocking=True)
                 ready[slot].record(copy_stream)
 
-        def e2e_step():
+        def run():
             i = state["i"]
             slot = i % 2
             enqueue_copy(1 - slot)                                   # next step's inputs overlap this step's compute
             torch.cuda.current_stream().wait_event(ready[slot])
-            o = graphs_e2e[slot].replay() if use_graph else dec(bufs[slot], THRESH)   # ends with the count read-back (host sync)
-            if world > 1:
-                shard.all_gather_batch(o[("disp", 0)], n_global)
-            disp_host.copy_(o[("disp", 0)], non_blocking=True)
+            o = graphs_e2e[slot].replay() if use_graph else dec(bufs[slot], THRESH)
+            disp_host.copy_(o[("disp", 0)], non_blocking=True)       # the step's result back to the host
             copy_stream.wait_stream(torch.cuda.current_stream())     # slot is free for the copy after next
             state["i"] = i + 1
-            last["e2e_out"] = o
+            return o
 
+        st = _Stepper(run, gather, lst)
         enqueue_copy(0)
-        ms_ = time_device(e2e_step, args.steps, 2, dist, world)
-        o = last.pop("e2e_out")
+        ms_ = time_device(st.step, args.steps, 2, dist, world, flush=st.flush)
+        o = lst["out"]
         h2d = sum(host[k].numel() * 4 for k in dma)
         in_place = 0
         for k in zero_copy:                                          # 128-byte requests the gated move issued to the host
             up = o[("upsample_mask", k)].reshape(n_local, -1)
             groups = int(up.reshape(n_local, -1, 32).any(-1).sum().item()) if up.shape[1] % 32 == 0 else up.numel() // 32
             in_place += groups * 128 * host[k].shape[1]
-        del graphs_e2e, bufs
+        del graphs_e2e, bufs, st
         torch.cuda.empty_cache()
         return ms_, h2d, in_place
 
     h2d_bytes = sum(f.numel() * 4 for f in host)
     e2e_ms, e2e_h2d, _ = run_e2e(())
     e2e_note = "pinned host features; H2D double-buffered on a copy stream; PCIe-bound"
+    e2e_variants = [{"zero_copy_maps": [], "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_bytes_per_step": e2e_h2d,
+                     "value": round(n_global * args.steps / (e2e_ms * 1e-3), 1)}]
     e2e_dma = None
     if args.e2e_zero_copy and args.e2e_zero_copy != "off":
-        # second variant: the finest skip map(s) stay in pinned host memory and the gated layout move reads only the
+        # further variants: the listed skip map(s) stay in pinned host memory and the gated layout move reads only the
         # 32-pixel groups under the level's upsample mask, in place, across PCIe (graphs captured with gated_layout on)
-        zc = tuple(int(k) for k in args.e2e_zero_copy.split(","))
         was = dec.gated_layout
         dec.gated_layout = True
-        zc_ms = None
+        best = None
         try:
-            with _Guard("e2e_zero_copy", world == 1, section_errors):
-                zc_ms, zc_h2d, zc_in_place = run_e2e(zc)
+            for spec in args.e2e_zero_copy.split(";"):
+                zc = tuple(int(k) for k in spec.split(","))
+                with _Guard("e2e_zero_copy_%s" % spec, world == 1, section_errors):
+                    zc_ms, zc_h2d, zc_in_place = run_e2e(zc)
+                    e2e_variants.append({"zero_copy_maps": list(zc), "ms_per_step": round(zc_ms / args.steps, 3),
+                                         "h2d_bytes_per_step": zc_h2d + zc_in_place, "dma_bytes": zc_h2d, "in_place_bytes": zc_in_place,
+                                         "value": round(n_global * args.steps / (zc_ms * 1e-3), 1)})
+                    log("[e2e] zero-copy skips %s: %.2f ms/step (%.0f MB DMA + %.0f MB in place) vs DMA-only %.2f ms/step"
+                        % (zc, zc_ms / args.steps, zc_h2d / 1e6, zc_in_place / 1e6, e2e_ms / args.steps))
+                    if best is None or zc_ms < best[0]:
+                        best = (zc_ms, zc_h2d, zc_in_place, zc)
         finally:
             dec.gated_layout = was
-        if zc_ms is None:                                            # the variant failed (N = 1 only): keep the DMA figure
-            zc_ms, zc_h2d, zc_in_place = float("inf"), 0, 0
-        if zc_ms != float("inf"):
-            log("[e2e] DMA %.2f ms/step (%.0f MB) ; zero-copy skips %s %.2f ms/step (%.0f MB DMA + %.0f MB in place)"
-                % (e2e_ms / args.steps, e2e_h2d / 1e6, zc, zc_ms / args.steps, zc_h2d / 1e6, zc_in_place / 1e6))
-        if zc_ms < e2e_ms:
+        if best is not None and best[0] < e2e_ms:
             e2e_dma = {"value": round(n_global * args.steps / (e2e_ms * 1e-3), 1), "unit": UNIT,
                        "h2d_bytes_per_step": e2e_h2d * world, "ms_per_step": round(e2e_ms / args.steps, 3),
                        "note": "every feature map DMA-copied whole (the plain path)"}
+            zc_ms, zc_h2d, zc_in_place, zc = best
             e2e_ms, e2e_h2d = zc_ms, zc_h2d + zc_in_place
             e2e_note = ("pinned host features; the other maps DMA-copied one step ahead on a copy stream, skip map(s) %s read in "
                         "place from pinned host memory by the gated layout move (only 32-pixel groups under the level's "
@@ -595,8 +751,8 @@ def run_native(args, rank, world, local_rank):
     torch.cuda.synchronize()
     ops.set_profiler(None)
     prof_records = prof.results()
-    roof, roof_all = roofline_from(prof_records, peak_gbs, peak_tf, peak_src, prof_steps, peak_tf_sus)
-    conv_layers = conv_layer_table(prof_records, peak_gbs, peak_tf, prof_steps)
+    roof, roof_all = roofline_from(prof_records, peak_gbs, peak_tf, peak_src, prof_steps, peak_tf_sus, tf32_peak)
+    conv_layers = conv_layer_table(prof_records, peak_gbs, tf32_peak, prof_steps)
 
     # ---- 4. secondary workload of the metric (device-resident only)
     also = None
@@ -607,23 +763,20 @@ def run_native(args, rank, world, local_rank):
             wl2, dec2, host2 = setup(ALSO)
             res2 = [f.to(dev) for f in host2]
             n2 = wl2["per_gpu_batch"] * world
-
             graph2 = graphs.GraphedSparseDecoder(dec2, res2, THRESH) if use_graph else None
-
-            def step2():
-                o = graph2.replay() if use_graph else dec2(res2, THRESH)
-                if world > 1:
-                    shard.all_gather_batch(o[("disp", 0)], n2)
-                last["out2"] = o
-
-            ms2 = time_device(step2, args.steps, max(args.warmup, 3), dist, world)
-            o2 = last["out2"]
+            lst2 = {}
+            st2 = _Stepper(graph2.replay if use_graph else (lambda: dec2(res2, THRESH)),
+                           shard.OverlappedGather(n2) if world > 1 else None, lst2)
+            ms2 = time_device(st2.step, args.steps, max(args.warmup, 3), dist, world, flush=st2.flush)
+            o2 = lst2["out"]
             also = {"workload": ALSO, "value": round(n2 * args.steps / (ms2 * 1e-3), 1), "unit": UNIT,
                     "ms_per_step": round(ms2 / args.steps, 3), "global_batch": n2,
                     "wavelet_mask_density": {str(s): round(float(o2[("wavelet_mask", s)].float().mean()), 4) for s in (3, 2, 1, 0)},
-                    "total_ops_per_frame": o2["total_ops"] / wl2["per_gpu_batch"]}
+                    "total_ops_per_frame": lst2["total_ops"] / wl2["per_gpu_batch"]}
+            del graph2, st2, res2
 
-    # ---- 4b. NYUv2 workload of configs[3]: DenseNet161 pyramid 640x480, 8 frames/GPU, SparseDecoderWave thr 0.1
+    # ---- 4b. NYUv2 workload of configs[3]: DenseNet161 pyramid 640x480, SparseDecoderWave thr 0.1, CUDA-graph replay.
+    # Weak-scaled (8 frames per GPU) and, on several GPUs, as the config is written: global batch 8 sharded 1 -> 8.
     also_nyu = None
     if args.workload == MAIN and not args.no_also:
         with _Guard("also_nyu", world == 1, section_errors):
@@ -633,35 +786,60 @@ def run_native(args, rank, world, local_rank):
             synth.load_random(nmod, seed=NYU["param_seed"], gains={k: SYNTH["head_gain"] for k in NYU["heads"]},
                               highpass=NYU["heads"])
             nmod = nmod.to(dev).eval()
-            nb = NYU["per_gpu_batch"]
-            nfeats = [f.to(dev) for f in synth.blocky_features(
-                synth.nyu_feature_shapes(nb, NYU["height"], NYU["width"], NYU["ch"]), seed=NYU["feat_seed"] + rank * nb,
-                cell=SYNTH["cell"], texture=SYNTH["texture"])]
-            n3 = nb * world
+            nmod.count_ops = "async"
 
-            def step3():
-                o = nmod(nfeats, NYU["thresh"])
-                if world > 1:
-                    shard.all_gather_batch(o[("disp", 0)], n3)
-                last["out3"] = o
-
-            ms3 = time_device(step3, args.steps, max(args.warmup, 3), dist, world)
-            o3 = last["out3"]
-            also_nyu = {"workload": NYU["name"], "value": round(n3 * args.steps / (ms3 * 1e-3), 1), "unit": UNIT,
-                        "ms_per_step": round(ms3 / args.steps, 3), "global_batch": n3, "thresh_ratio": NYU["thresh"],
-                        "launch_mode": "eager", "decoder": "SparseDecoderWave (NYUv2/networks/decoders/densedepth_decoder.py:224-409), batched",
+            def nyu_run(nb, first):
+                nfeats = [f.to(dev) for f in synth.blocky_features(
+                    synth.nyu_feature_shapes(nb, NYU["height"], NYU["width"], NYU["ch"]), seed=NYU["feat_seed"] + first,
+                    cell=SYNTH["cell"], texture=SYNTH["texture"])]
+                n3 = nb * world
+                g3 = graphs.GraphedSparseDecoder(nmod, nfeats, NYU["thresh"]) if use_graph else None
+                lst3 = {}
+                st3 = _Stepper(g3.replay if use_graph else (lambda: nmod(nfeats, NYU["thresh"])),
+                               shard.OverlappedGather(n3) if world > 1 else None, lst3)
+                ms3 = time_device(st3.step, args.steps, max(args.warmup, 3), dist, world, flush=st3.flush)
+                o3 = lst3["out"]
+                return {"value": round(n3 * args.steps / (ms3 * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms3 / args.steps, 3),
+                        "global_batch": n3, "per_gpu_batch": nb,
                         "wavelet_mask_density": {str(s_): round(float(o3[("wavelet_mask", s_)].float().mean()), 4) for s_ in (2, 1, 0)},
-                        "total_ops_per_frame": o3["total_ops"] / nb, "dense_total_ops_per_frame": 33463546800}
-            del nmod, nfeats
+                        "total_ops_per_frame": lst3["total_ops"] / nb}
 
-    # ---- 5. CPU baseline (rank 0, N == 1 only)
-    cpu = None
+            nb = NYU["per_gpu_batch"]
+            also_nyu = {"workload": NYU["name"], "thresh_ratio": NYU["thresh"],
+                        "launch_mode": "CUDA graph replay" if use_graph else "eager",
+                        "decoder": "SparseDecoderWave (NYUv2/networks/decoders/densedepth_decoder.py:224-409), batched",
+                        "dense_total_ops_per_frame": 33463546800}
+            also_nyu.update(nyu_run(nb, rank * nb))
+            also_nyu["scaling"] = "weak (8 frames per GPU)"
+            if world > 1 and nb % world == 0:
+                per = nb // world
+                strong = nyu_run(per, rank * per)
+                strong["scaling"] = "strong: configs[3] as written, global batch 8 sharded over %d GPUs (%d frame(s) each; latency-bound)" % (world, per)
+                also_nyu["as_written_global_bs8"] = strong
+            del nmod
+
+    # ---- 5. CPU baseline + parity block (rank 0, N == 1 only)
+    cpu, parity_block = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
-        fps, times = cpu_frames_per_sec(args.workload, args.cpu_frames, budget_s=20.0, batch=host)
+        from oracle import parity
+        reports, seen = [], set()
+
+        def on_frame(b, ref):
+            if b in seen:
+                return
+            seen.add(b)
+            reports.append(parity.compare_kitti_sample(parity.sample_of(out_host, b), ref, THRESH))
+
+        fps, times = cpu_frames_per_sec(args.workload, args.cpu_frames, budget_s=20.0, batch=host, on_frame=on_frame)
         cpu = {"value": round(fps, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d frames of %s (the GPU arm's own %d-frame step, cycled), one at a time as the reference "
                          "requires; %.1fs of CPU work; intra-op threads chosen by probe out of %d usable cores"
                          % (len(times), args.workload, n_local, sum(times), _affinity_cores())}
+        parity_block = parity.merge_reports(reports)
+        parity_block["what"] = ("the timed step's own GPU outputs (every disp / wavelet plane, all five masks per scale, "
+                                "total_ops) vs the oracle's outputs for the same frames, which the cpu_baseline leg computes "
+                                "anyway; float bar 1e-4 relative, masks exact up to reported threshold ties (oracle/parity.py); "
+                                "Haar bit-parity with pytorch_wavelets proper is unpinned (package absent), pinned algebraically")
 
     launches_t = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
@@ -671,18 +849,14 @@ def run_native(args, rank, world, local_rank):
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": args.workload, "global_batch": n_global, "per_gpu_batch": n_local,
-                "encoder": "ResNet50 pyramid %s" % (list(wl["ch"]),), "resolution": "%dx%d" % (wl["width"], wl["height"]),
-                "thresh_ratio": THRESH, "decoder": "SparseDepthWaveProgressiveDecoder (levels 3,2,1 sparse)",
-                "parallelism": "dp%d batch-sharded, one all-gather of disp0" % world,
-                "l2": "inputs larger than L2: %.2f GB of features read per step per GPU" % (h2d_bytes / 1e9),
+            "config": workload_config(args.workload, world),
+            "workload_stats": {
                 "wavelet_mask_density": {str(k): v for k, v in dens.items()},
                 "total_ops_per_frame": ops_per_frame, "dense_total_ops_per_frame": 17473692295 if args.workload == MAIN else None,
-                "weights": "seeded random init, high-pass coefficient heads x%.0f (synth.py)" % SYNTH["head_gain"],
-                "features": "seeded blocky maps, cell %d px, texture %.2f" % (SYNTH["cell"], SYNTH["texture"]),
-                "timed_region": "decoder forward on NCHW fp32 features resident in HBM, incl. layout transposes, "
-                                "mask/compaction, the total_ops count read-back and (N>1) the all-gather",
+                "timed_region": "decoder forward on NCHW fp32 features resident in HBM, incl. layout transposes, mask / "
+                                "compaction kernels, the count read-back behind total_ops (asynchronous: evaluated one step "
+                                "later, the last one inside the region) and (N>1) the all-gather of disp0 (started per step, "
+                                "overlapped with the next step, the last one inside the region)",
                 "launch_mode": "CUDA graph replay (graphs.GraphedSparseDecoder)" if use_graph else "eager",
                 "head_1x1_stages": "fused (head_mlp) on levels 2, 1" if dec.fused_heads else "two gather-GEMM launches per level",
                 "layout_moves": "%s, %s" % ("gated by the upsample mask" if dec.gated_layout else "whole maps",
@@ -692,15 +866,21 @@ def run_native(args, rank, world, local_rank):
                             "note": "same step issued launch by launch from Python (no CUDA graph)"},
             "value_channels_last": {"value": round(value_cl, 1), "unit": UNIT, "ms_per_step": round(ms_cl / args.steps, 3),
                                     "note": "same step, encoder features in torch.channels_last: used zero-copy, no layout transposes"},
+            "allgather_ms": round(allgather_ms, 3) if allgather_ms is not None else None,
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": e2e_h2d * world,
                     "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": round(e2e_ms / args.steps, 3),
-                    "note": e2e_note + ("; byte counts are the whole job's (rank 0's x %d ranks)" % world if world > 1 else "")},
+                    "pcie_floor_ms": round(e2e_h2d / 57e9 * 1e3, 2),
+                    "note": e2e_note + "; pcie_floor_ms = h2d bytes / 57 GB/s (what cudaMemcpyAsync from pinned memory "
+                            "sustains on this box)" + ("; byte counts are the whole job's (rank 0's x %d ranks)" % world if world > 1 else "")},
             "e2e_dma": e2e_dma,
+            "e2e_variants": e2e_variants,
             "gpu_launches": int(launches_t.item()),
             "clocks": clocks,
             "roofline": roof,
             "roofline_kernels": roof_all,
             "conv_layers": conv_layers,
+            "sweep": sweep,
+            "parity": parity_block,
             "cpu_baseline": cpu,
             "also": also,
             "also_nyu": also_nyu,
@@ -721,10 +901,12 @@ def main():
     ap.add_argument("--workload", default=MAIN, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-frames", type=int, default=400)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-zero-copy", default=os.environ.get("WMD_E2E_ZERO_COPY", "0"),
-                    help="comma list of skip-map indices (default 0 = the finest) that the second e2e variant leaves in "
-                         "pinned host memory for the gated layout move to read in place; 'off' skips that variant")
+    ap.add_argument("--e2e-zero-copy", default=os.environ.get("WMD_E2E_ZERO_COPY", "0;0,1,2"),
+                    help="';'-separated variants, each a comma list of skip-map indices that the variant leaves in pinned "
+                         "host memory for the gated layout move to read in place (default: the finest map, then all three "
+                         "sparse levels' maps); the fastest variant is reported as e2e; 'off' skips them")
     ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the threshold sweep (configs[2] / configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -414,3 +414,90 @@ def test_factored_ll_head_matches_the_direct_head_kernel():
         assert rel_err(got[("disp", s)], want[("disp", s)]) <= 1e-5, s
         flips = float((got[("wavelet_mask", s)] != want[("wavelet_mask", s)]).float().mean())
         assert flips <= 1e-4, (s, flips)
+
+
+# ------------------------------------------------------------------------------------------ host-side behaviour added in round 2
+def test_async_op_count_future_equals_the_synchronous_ints_eager_and_graphed():
+    """count_ops = "async": out["total_ops"] is an OpsFuture (no host wait in forward / replay); its result() carries
+    exactly the keys and values the synchronous mode stores in the output dict."""
+    from wavelet_monodepth_b200 import graphs
+    from wavelet_monodepth_b200.opsfuture import OpsFuture
+    mod, _, feats = _full_kitti(synth.RESNET18_CH, 3, 192, 640)
+    sync = mod(feats, 0.05)
+    mod.count_ops = "async"
+    try:
+        out = mod(feats, 0.05)
+        assert isinstance(out["total_ops"], OpsFuture) and ("total_ops", 0) not in out
+        res = out["total_ops"].result()
+        for k in ("total_ops", "total_ops_per_sample", ("total_ops", 0), ("total_ops", 1), ("total_ops", 2), ("total_ops", 3)):
+            assert res[k] == sync[k], k
+        assert int(out["total_ops"]) == sync["total_ops"]
+        g = graphs.GraphedSparseDecoder(mod, feats, 0.05)
+        futs = [g.replay()["total_ops"] for _ in range(7)]           # more replays in flight than pinned ring slots
+        assert all(f.result()["total_ops"] == sync["total_ops"] for f in futs)
+    finally:
+        mod.count_ops = True
+    nmod = nd.SparseDecoderWave(enc_features=[16, 16, 32, 64, 128], decoder_width=0.5)
+    synth.load_random(nmod, seed=5, gains={"wave": 4.0})
+    nmod = nmod.to(DEV).eval()
+    nfeats = [torch.rand(s, device=DEV) for s in synth.nyu_feature_shapes(2, 96, 128, [16, 16, 32, 64, 128])]
+    want = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in nmod(nfeats, 0.1).items()}
+    g = graphs.GraphedSparseDecoder(nmod, nfeats, 0.1)                # NYU decoder under a CUDA graph
+    got = g.replay()
+    for k, v in want.items():
+        assert (torch.equal(got[k], v) if torch.is_tensor(v) else got[k] == v), key_str(k)
+
+
+def test_invalidate_packs_after_a_data_write_the_version_counter_cannot_see():
+    _, meta = load_golden("kitti_tiny_dense")
+    mod, _ = _kitti(kd.DepthWaveProgressiveDecoder, meta)
+    feats = kitti_features(meta, DEV)
+    with torch.no_grad():
+        a = mod(feats)[("disp", 0)].clone()
+        for p in mod.parameters():
+            p.data.mul_(1.05)                                         # invisible to p._version
+        mod.invalidate_packs()
+        b = mod(feats)[("disp", 0)].clone()
+        assert float((a - b).abs().max()) > 1e-4
+        sd = {k: v * 0.5 for k, v in mod.state_dict().items() if k.endswith("weight")}
+        mod.load_state_dict(sd, strict=False)                         # post-hook invalidates
+        c = mod(feats)[("disp", 0)]
+        assert float((b - c).abs().max()) > 1e-4
+
+
+def test_empty_batch_returns_empty_outputs_with_the_right_keys():
+    mod, _, feats = _full_kitti(synth.RESNET18_CH, 2, 192, 640)
+    out = mod([f[:0] for f in feats], 0.05)
+    assert out[("disp", 0)].shape == (0, 1, 192, 640) and out[("wavelet_mask", 1)].shape == (0, 1, 48, 160)
+    assert out["total_ops"] == 0
+    _, pix, off = ops.compact(torch.zeros((0, 1, 8, 8), dtype=torch.uint8, device=DEV))
+    assert off.tolist() == [0] and pix.numel() == 0
+
+
+def test_nan_coefficients_never_set_the_mask_like_torch_max():
+    """torch.abs(yh).max(2)[0] > thresh is False where a band is NaN, and a NaN in yl makes every test False."""
+    yh = torch.rand(2, 3, 16, 24, device=DEV) + 1.0
+    yh[0, 1, 3, 4] = float("nan")
+    yl = torch.rand(2, 1, 32, 48, device=DEV)
+    yl[1, 0, 5, 5] = float("nan")
+    thresh = ops.range_thresh(yl, 0.05)
+    assert bool(torch.isnan(thresh[1])) and not bool(torch.isnan(thresh[0]))
+    m = ops.level_masks(yh, thresh)
+    want0 = (yh[0].abs().max(0)[0] > thresh[0])
+    assert torch.equal(m["S0"][0, 0].bool(), want0) and not bool(m["S0"][0, 0, 3, 4])
+    assert not bool(m["S0"][1].any())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_decoder_on_a_non_current_device():
+    """model.to('cuda:1') while cuda:0 is current - kernels must launch on the tensors' device."""
+    mod, _, feats = _full_kitti(synth.RESNET18_CH, 2, 192, 640)
+    want = mod(feats, 0.05)
+    mod1 = mod.to("cuda:1")
+    feats1 = [f.to("cuda:1") for f in feats]
+    assert torch.cuda.current_device() == 0
+    got = mod1(feats1, 0.05)
+    assert got[("disp", 0)].device.index == 1
+    for s in range(4):
+        assert torch.equal(got[("disp", s)].cpu(), want[("disp", s)].cpu())
+    assert got["total_ops"] == want["total_ops"]

@@ -35,6 +35,20 @@ def _worker(rank, world, port, n_global, result_dir):
         assert local[0].shape[0] == hi - lo
         out, full = shard.sharded_decode(lambda f: okitti.dense_forward(sd, f), local, n_global)
         assert full.shape[0] == n_global
+        # the overlapped form: three "steps" whose local output buffer is overwritten right after start() - what a
+        # CUDA-graph replay does - each gathered through the double-buffered staging slots
+        og = shard.OverlappedGather(n_global)
+        buf = torch.empty_like(out[("disp", 0)])
+        handles, wants = [], []
+        for k in range(3):
+            buf.copy_(out[("disp", 0)] * (k + 1))
+            handles.append(og.start(buf))
+            buf.fill_(-1.0)                                # the producer moves on before the gather is consumed
+            wants.append(full * (k + 1))
+            if k >= 1:                                     # consume step k-1 while step k is in flight
+                got = handles[k - 1].wait()
+                assert torch.equal(got, wants[k - 1]), ("overlapped gather", k - 1)
+        assert torch.equal(handles[2].wait(), wants[2])
         if rank == 0:
             ref = okitti.dense_forward(sd, feats)[("disp", 0)]
             torch.save({"full": full, "ref": ref}, os.path.join(result_dir, "r0_%d.pt" % n_global))

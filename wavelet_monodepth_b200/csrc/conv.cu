@@ -221,11 +221,11 @@ static int launch_conv(const wmd_conv_desc& d, cudaStream_t stream) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {   // outside the cache: set it on every launch
     int rc = record(cudaFuncSetAttribute(conv_rows_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(Cfg::SMEM)));
     if (rc != WMD_OK) return rc;
-    attr_done[dev] = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const long long tiles = static_cast<long long>(ceil_div(d.max_rows, Cfg::BM)) * ceil_div(d.cout, Cfg::BN);
   const long long cap = static_cast<long long>(sm_count()) * 2;

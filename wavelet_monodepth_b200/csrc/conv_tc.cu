@@ -806,11 +806,11 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {   // outside the cache: set it on every launch
     int rc = record(cudaFuncSetAttribute(conv_rows_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(Cfg::SMEM)));
     if (rc != WMD_OK) return rc;
-    attr_done[dev] = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN) * (splits > 0 ? splits : 1);
   const long long cap = sm_count();

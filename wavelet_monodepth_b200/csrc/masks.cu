@@ -19,10 +19,15 @@ static inline int range_blocks(long long per_sample) {
   return static_cast<int>(b);
 }
 
+// torch.max / torch.min PROPAGATE NaN (fminf / fmaxf drop it): a NaN anywhere in yl makes the reference's threshold
+// NaN and every `> thresh` test false (depth_decoder.py:308-309).  Same here.
+__device__ __forceinline__ float nan_min(float a, float b) { return (a != a || b != b) ? NAN : fminf(a, b); }
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? NAN : fmaxf(a, b); }
+
 __device__ __forceinline__ void block_minmax(float& mn, float& mx, float* smn, float* smx) {
   for (int o = 16; o > 0; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
@@ -32,8 +37,8 @@ __device__ __forceinline__ void block_minmax(float& mn, float& mx, float* smn, f
     mn = lane < nw ? smn[lane] : INFINITY;
     mx = lane < nw ? smx[lane] : -INFINITY;
     for (int o = 16; o > 0; o >>= 1) {
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
   }
   __syncthreads();
@@ -58,15 +63,15 @@ __global__ void __launch_bounds__(kRangeThreads) range_thresh_kernel(const float
     for (long long i = static_cast<long long>(b) * blockDim.x + threadIdx.x; i < nv;
          i += static_cast<long long>(B) * blockDim.x) {
       const float4 v = __ldg(xv + i);
-      mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
-      mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+      mn = nan_min(nan_min(mn, v.x), nan_min(v.y, nan_min(v.z, v.w)));
+      mx = nan_max(nan_max(mx, v.x), nan_max(v.y, nan_max(v.z, v.w)));
     }
   } else {
     for (long long i = static_cast<long long>(b) * blockDim.x + threadIdx.x; i < per_sample;
          i += static_cast<long long>(B) * blockDim.x) {
       const float v = __ldg(xs + i);
-      mn = fminf(mn, v);
-      mx = fmaxf(mx, v);
+      mn = nan_min(mn, v);
+      mx = nan_max(mx, v);
     }
   }
   block_minmax(mn, mx, smn, smx);
@@ -83,8 +88,8 @@ __global__ void __launch_bounds__(kRangeThreads) range_thresh_kernel(const float
   mn = INFINITY; mx = -INFINITY;
   const volatile float* pr = partial + static_cast<long long>(n) * B * 2;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    mn = fminf(mn, pr[2 * i]);
-    mx = fmaxf(mx, pr[2 * i + 1]);
+    mn = nan_min(mn, pr[2 * i]);
+    mx = nan_max(mx, pr[2 * i + 1]);
   }
   block_minmax(mn, mx, smn, smx);
   if (threadIdx.x == 0) {
@@ -119,7 +124,8 @@ __global__ void __launch_bounds__(256) level_masks_kernel(const float* __restric
         v = 1;
       } else {
         const long long o = static_cast<long long>(y) * W + x;
-        const float m = fmaxf(fmaxf(fabsf(__ldg(ph + o)), fabsf(__ldg(ph + HW + o))), fabsf(__ldg(ph + 2 * HW + o)));
+        // torch.abs(yh).max(2)[0] > thresh: the band maximum propagates NaN, and NaN > thresh is false
+        const float m = nan_max(nan_max(fabsf(__ldg(ph + o)), fabsf(__ldg(ph + HW + o))), fabsf(__ldg(ph + 2 * HW + o)));
         v = m > th ? 1 : 0;
       }
     }
@@ -319,8 +325,12 @@ extern "C" size_t wmd_compact_ws_bytes(int N, int H, int W) {
 extern "C" int wmd_compact_mask(const uint8_t* mask, int32_t* idxmap, int32_t* pixels, int32_t* offsets, int N, int H,
                                 int W, void* ws, size_t ws_bytes, wmd_stream_t stream) {
   using namespace wmd;
+  WMD_REQUIRE(N >= 0 && H > 0 && W > 0, WMD_ERR_SHAPE);
+  if (N == 0) {                                   // an empty shard (world size > batch): no rows, offsets = [0]
+    if (offsets) return record(cudaMemsetAsync(offsets, 0, sizeof(int32_t), as_stream(stream)));
+    return WMD_OK;
+  }
   WMD_REQUIRE(mask && ws, WMD_ERR_ARG);
-  WMD_REQUIRE(N > 0 && H > 0 && W > 0, WMD_ERR_SHAPE);
   const long long total = static_cast<long long>(N) * H * W;
   WMD_REQUIRE(total < (1ll << 31), WMD_ERR_SHAPE);
   WMD_REQUIRE(ws_bytes >= wmd_compact_ws_bytes(N, H, W), WMD_ERR_WORKSPACE);

@@ -26,19 +26,35 @@ import torch
 import torch.nn as nn
 
 from . import opcount, ops
+from .opsfuture import OpsFuture
 from ._lib import ACT_ELU, ACT_LRELU, ACT_SIGMOID, PAD_REFLECT, WmdError
 from .kitti_layers import Conv1x1, Conv3x3, ConvBlock, upsample
 from .wavelets import IDWT
 
 
+def _version_of(t):
+    try:
+        return t._version
+    except RuntimeError:          # inference tensors do not track versions
+        return -1
+
+
 class _PackCache:
-    """Packed-weight cache keyed by (data_ptr, version) of the source parameters."""
+    """Packed-weight cache keyed by (data_ptr, version, device) of the source parameters.
+
+    In-place updates through autograd-visible ops (optimizer steps, ``p.mul_()``) bump the version counter and
+    repack on the next forward.  Updates the counter cannot see - ``p.data.copy_()``, an EMA swap through ``.data``,
+    tensors created under ``inference_mode`` - need ``invalidate()``; the decoders call it from ``_apply`` (``.to()``,
+    ``.cuda()``, ``.half()``...) and from a ``load_state_dict`` post-hook, and expose it as ``invalidate_packs()``."""
 
     def __init__(self):
         self._c = {}
 
+    def invalidate(self):
+        self._c.clear()
+
     def get(self, key, tensors, build):
-        ver = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors)
+        ver = tuple((t.data_ptr(), _version_of(t), str(t.device)) for t in tensors)
         ent = self._c.get(key)
         if ent is None or ent[0] != ver:
             with torch.no_grad():
@@ -141,6 +157,7 @@ class _WaveDecoderBase(nn.Module):
         self.decoder = nn.ModuleList(list(self.convs.values()))
         self.sigmoid = nn.Sigmoid()
         self._packs = _PackCache()
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packs())
         # optional fused consumer epilogue (not part of the reference's decoder, off by default): when set to (H, W),
         # inference also returns ("disp_full", s) = F.interpolate(("disp", s), (H, W), mode="bilinear",
         # align_corners=False) for s = 1..3 - what KITTI/trainer.py:338-339 computes from every scale - produced
@@ -158,6 +175,16 @@ class _WaveDecoderBase(nn.Module):
         self.overlap_compaction = os.environ.get("WMD_OVERLAP_COMPACTION", "1") == "1"
 
     # ---- packed parameters ------------------------------------------------------------------
+    def invalidate_packs(self):
+        """Drop the packed copies of the weights (they are rebuilt on the next native forward).  Needed only after a
+        weight update the version counters cannot see, e.g. ``p.data.copy_(...)``."""
+        self._packs.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        if hasattr(self, "_packs"):
+            self._packs.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
     def _upconv(self, i, j):
         conv = self.convs[("upconv", i, j)].conv.conv
         c1 = int(self.num_ch_enc[i - 1]) if j == 1 else 0          # upconv(i,1) reads the skip map as gather source 1
@@ -221,13 +248,39 @@ class _WaveDecoderBase(nn.Module):
     def _native_forward(self, feats, thresh_ratio, sparse_levels, with_masks):
         """Runs levels 4..1 on libwmd.  sparse_levels: set of levels i executed on active lists.
 
-        Returns (outputs, count_tensors) where count_tensors[i] = (off2, off4, off5) device int32 (N+1,)
-        for sparse levels (None for dense ones)."""
+        Returns (outputs, counts): counts = int32 device tensor (levels, 3, N+1) with the row offsets of the compacted
+        sets S2, S4, S5 of every sparse level, sparse levels in descending order (None without sparse levels)."""
+        dev = next(f.device for f in feats if f.is_cuda) if any(f.is_cuda for f in feats) else None
+        if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):       # libwmd launches on the current device: make the tensors' device current
+                return self._native_forward_on_device(feats, thresh_ratio, sparse_levels, with_masks)
+        return self._native_forward_on_device(feats, thresh_ratio, sparse_levels, with_masks)
+
+    def _empty_outputs(self, feats, sparse_levels, with_masks):
+        """Outputs of an empty batch (a rank whose shard is empty: world size > batch) - right keys, N = 0."""
+        dev = feats[-1].device
+        out = {}
+        h, w = (int(v) for v in feats[4].shape[2:])
+        for i in range(4, 0, -1):
+            if with_masks:
+                for name, up in (("lowres_mask", 0), ("upconv0_mask", 0), ("upsample_mask", 1), ("upconv1_mask", 1),
+                                 ("wavelet_mask", 1)):
+                    out[(name, i - 1)] = torch.zeros((0, 1, h << up, w << up), dtype=torch.bool, device=dev)
+            for band in ("LL", "LH", "HL", "HH"):
+                out[("wavelets", i - 1, band)] = torch.zeros((0, 1, 2 * h, 2 * w), dtype=torch.float32, device=dev)
+            out[("disp", i - 1)] = torch.zeros((0, 1, 4 * h, 4 * w), dtype=torch.float32, device=dev)
+            h, w = 2 * h, 2 * w
+        counts = torch.zeros((len(sparse_levels), 3, 1), dtype=torch.int32, device=dev) if sparse_levels else None
+        return out, counts
+
+    def _native_forward_on_device(self, feats, thresh_ratio, sparse_levels, with_masks):
         # with gated_layout the skip map of a sparse level i (feats[i-1]) may live in pinned host memory
         _need_cuda(feats, host_ok=tuple(i - 1 for i in sparse_levels) if self.gated_layout else ())
         out = {}
         n = feats[-1].shape[0]
         dev = feats[-1].device
+        if n == 0:
+            return self._empty_outputs(feats, sparse_levels, with_masks)
         x_rows, x_c, prev_map = ops.nchw_to_rows(feats[4]), feats[4].shape[1], None
         # layout moves of the skip maps (NCHW -> pixel-major rows), two options on top of the plain in-order transpose:
         #  gated_layout   a sparse level reads its skip map only under the upsample mask S3 (sparse_upsample:
@@ -340,7 +393,8 @@ class _WaveDecoderBase(nn.Module):
             out[("disp", i - 1)] = disp
             x_rows, x_c = xb, c
             h, w = 2 * h, 2 * w
-        return out, counts
+        stacked = torch.stack([torch.stack(counts[i]) for i in sorted(counts, reverse=True)]) if counts else None
+        return out, stacked
 
 
 class DepthWaveProgressiveDecoder(_WaveDecoderBase):
@@ -396,8 +450,10 @@ class DepthWaveProgressiveDecoder(_WaveDecoderBase):
 class SparseDepthWaveProgressiveDecoder(_WaveDecoderBase):
     """Threshold-gated sparse wavelet decoder, batched.  [depth_decoder.py:171-428]
 
-    Inference only, like the reference (KITTI/trainer.py:35-36).  ``count_ops=False`` skips the one host
-    read of the active counts (then ``total_ops`` keys are omitted).
+    Inference only, like the reference (KITTI/trainer.py:35-36).  ``count_ops``: True (default) returns the
+    reference's ``total_ops`` keys as Python ints, which waits for this forward's active counts; ``"async"`` returns
+    ``out["total_ops"]`` as an ``OpsFuture`` instead and never blocks the host (serving / multi-GPU: the next step
+    and the all-gather are enqueued while this one runs); False skips op counting.
     """
 
     def __init__(self, num_ch_enc, scales=range(4), num_output_channels=1, use_skips=True):
@@ -416,39 +472,59 @@ class SparseDepthWaveProgressiveDecoder(_WaveDecoderBase):
 
     def forward(self, input_features, thresh_ratio=0.05, sparse_scales=[0, 1, 2, 3]):
         assert self.use_skips
-        sparse_levels = tuple(i for i in range(1, 4) if i in sparse_scales)
-        if any((i + 1) in sparse_levels and i not in sparse_levels for i in range(1, 4)):
-            raise NotImplementedError("a dense level below a sparse level is not defined by the reference either")
+        sparse_levels = self._sparse_levels(sparse_scales)
         out, counts = self._native_forward(input_features, float(thresh_ratio), sparse_levels, with_masks=True)
-        if self.count_ops:
-            self._add_total_ops(out, counts, input_features)
+        self._attach_total_ops(out, counts, input_features, sparse_levels)
         self.outputs = out
         return out
 
-    def _add_total_ops(self, out, counts, feats):
-        n = feats[-1].shape[0]
-        host = {}
-        if counts:
-            levels = sorted(counts)
-            flat = torch.stack([torch.stack(counts[i]) for i in levels]).cpu().numpy().astype(np.int64)   # one sync
-            for k, i in enumerate(levels):
-                host[i] = flat[k]                                  # (3, N+1)
-        per_sample = [0] * n
-        h4, w4 = feats[-1].shape[2:]
-        for i in range(4, 0, -1):
-            h, w = h4 << (4 - i), w4 << (4 - i)
-            cin0 = int(self.num_ch_enc[-1]) if i == 4 else int(self.num_ch_dec[i + 1])
-            c, cs = int(self.num_ch_dec[i]), int(self.num_ch_enc[i - 1])
-            level_total = 0
-            for b in range(n):
-                if i in host:
-                    m2, m4, m5 = (int(host[i][k][b + 1] - host[i][k][b]) for k in range(3))
-                    v = opcount.kitti_level_ops(i, h, w, cin0, c, cs, True, m2, m4, m5)
-                else:
-                    v = opcount.kitti_level_ops(i, h, w, cin0, c, cs, False)
-                per_sample[b] += v
-                level_total += v
-            out[("total_ops", i - 1)] = level_total
-        out["total_ops"] = sum(per_sample)
-        if n > 1:
-            out["total_ops_per_sample"] = per_sample
+    @staticmethod
+    def _sparse_levels(sparse_scales):
+        sparse_levels = tuple(i for i in range(1, 4) if i in sparse_scales)
+        if any((i + 1) in sparse_levels and i not in sparse_levels for i in range(1, 4)):
+            raise NotImplementedError("a dense level below a sparse level is not defined by the reference either")
+        return sparse_levels
+
+    def _attach_total_ops(self, out, counts, feats, sparse_levels):
+        """count_ops True: the reference's keys as Python ints (one wait for this forward's counts);
+        "async": out["total_ops"] = OpsFuture, nothing waits; False: no op counting."""
+        if not self.count_ops:
+            return
+        fut = self.ops_future(counts, feats, sparse_levels)
+        if self.count_ops == "async":
+            out["total_ops"] = fut
+        else:
+            out.update(fut.result())
+
+    def ops_future(self, counts, feats, sparse_levels):
+        """OpsFuture of one forward: enqueues the count read-back on the current stream (no host wait)."""
+        n = int(feats[-1].shape[0])
+        h4, w4 = (int(v) for v in feats[-1].shape[2:])
+        levels = sorted(sparse_levels, reverse=True)
+        ch_enc = [int(v) for v in self.num_ch_enc]
+        ch_dec = [int(v) for v in self.num_ch_dec]
+
+        def finish(host):
+            res = {}
+            per_sample = [0] * n
+            for i in range(4, 0, -1):
+                h, w = h4 << (4 - i), w4 << (4 - i)
+                cin0 = ch_enc[-1] if i == 4 else ch_dec[i + 1]
+                c, cs = ch_dec[i], ch_enc[i - 1]
+                level_total = 0
+                for b in range(n):
+                    if i in levels:
+                        row = host[levels.index(i)]                                  # (3, N+1) offsets of S2, S4, S5
+                        m2, m4, m5 = (int(row[k][b + 1] - row[k][b]) for k in range(3))
+                        v = opcount.kitti_level_ops(i, h, w, cin0, c, cs, True, m2, m4, m5)
+                    else:
+                        v = opcount.kitti_level_ops(i, h, w, cin0, c, cs, False)
+                    per_sample[b] += v
+                    level_total += v
+                res[("total_ops", i - 1)] = level_total
+            res["total_ops"] = sum(per_sample)
+            if n > 1:
+                res["total_ops_per_sample"] = per_sample
+            return res
+
+        return OpsFuture(counts if levels else None, finish)

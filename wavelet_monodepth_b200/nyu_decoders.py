@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import opcount, ops
+from .opsfuture import OpsFuture
 from ._lib import ACT_LRELU, ACT_NONE, PAD_REFLECT, PAD_REPLICATE, PAD_ZERO, WmdError
 from .kitti_decoders import _PackCache, _need_cuda, _pm
 from .kitti_layers import (make_result, mask2idxmap, mask2yx, sparse_conv3x3, sparse_select,  # noqa: F401
@@ -101,6 +102,16 @@ class _NyuWaveBase(nn.Module):
         self.wave3 = Conv3x3(features // 8, 3, padding=wave_pad, is_depthwise=dw_waveconv)
         self._depthwise = bool(dw_waveconv or dw_upconv)
         self._packs = _PackCache()
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packs())
+
+    def invalidate_packs(self):
+        """Drop the packed weight copies (see kitti_decoders._PackCache)."""
+        self._packs.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        if hasattr(self, "_packs"):
+            self._packs.invalidate()
+        return super()._apply(fn, *args, **kwargs)
 
     def _gemm(self, name, layer, c1=0):
         conv = layer.conv
@@ -113,10 +124,20 @@ class _NyuWaveBase(nn.Module):
 
     @torch.no_grad()
     def _native_forward(self, blocks, thresh_ratio, sparse):
-        """conv2/up1/wave1 dense, then the up2/wave2 and up3/wave3 levels dense or on active lists."""
+        """conv2/up1/wave1 dense, then the up2/wave2 and up3/wave3 levels dense or on active lists.
+
+        Returns (outputs, counts): counts = int32 device tensor (2, 2, N+1), row offsets of S4 / S5 of the two sparse
+        blocks (None on the dense path)."""
         _need_cuda(blocks)
         if self._depthwise:
             raise NotImplementedError("depthwise-separable variants only run on the differentiable cuDNN path")
+        dev = blocks[-1].device
+        if dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):       # libwmd launches on the current device
+                return self._native_forward_on_device(blocks, thresh_ratio, sparse)
+        return self._native_forward_on_device(blocks, thresh_ratio, sparse)
+
+    def _native_forward_on_device(self, blocks, thresh_ratio, sparse):
         out = {}
         xb = blocks[-1]
         n, _, h, w = xb.shape
@@ -125,6 +146,8 @@ class _NyuWaveBase(nn.Module):
         wp, b = self._gemm("conv2", self.conv2)
         d0 = ops.conv_rows(ops.nchw_to_rows(xb), xb.shape[1], wp, b, f, n, h, w, pad=PAD_REPLICATE, act=ACT_NONE)
         skip = blocks[-2]
+        if tuple(skip.shape[2:]) != (2 * h, 2 * w):
+            raise WmdError("skip block has shape %s, expected spatial %s" % (tuple(skip.shape), (2 * h, 2 * w)))
         wp, b = self._gemm("up1", self.up1.convA, skip.shape[1])
         d1 = ops.conv_rows(d0, f, wp, b, f // 2, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_LRELU, act_param=0.2,
                            shift0=1, x1=ops.nchw_to_rows(skip), c1=skip.shape[1])
@@ -185,7 +208,7 @@ class _NyuWaveBase(nn.Module):
                 out[("disp", 0)] = ll
             x_rows, x_c = xa, cout
             h, w = 2 * h, 2 * w
-        return out, counts
+        return out, (torch.stack([torch.stack(c) for c in counts]) if counts else None)
 
 
 class DecoderWave(_NyuWaveBase):
@@ -248,19 +271,127 @@ class SparseDecoderWave(_NyuWaveBase):
     def forward(self, x_blocks, thresh_ratio=0.1):
         out, counts = self._native_forward(x_blocks, float(thresh_ratio), sparse=True)
         if self.count_ops:
-            xb = x_blocks[-1]
-            n, cin, h, w = xb.shape
-            f = self.features
-            host = torch.stack([torch.stack(c) for c in counts]).cpu().numpy()       # (2, 2, N+1): one sync
+            fut = self.ops_future(counts, x_blocks)
+            if self.count_ops == "async":
+                out["total_ops"] = fut                       # OpsFuture: nothing waits (see opsfuture.py)
+            else:
+                out.update(fut.result())
+        return out
+
+    def ops_future(self, counts, x_blocks):
+        """OpsFuture of one forward: enqueues the count read-back on the current stream (no host wait)."""
+        n, cin, h, w = (int(v) for v in x_blocks[-1].shape)
+        f = self.features
+        c2, c3, c4 = (int(x_blocks[k].shape[1]) for k in (-2, -3, -4))
+
+        def finish(host):                                    # host: (2, 2, N+1) offsets of S4 / S5 per sparse block
             per_sample = []
             for b in range(n):
-                v = opcount.nyu_dense_part_ops(cin, h, w, f, x_blocks[-2].shape[1])
+                v = opcount.nyu_dense_part_ops(cin, h, w, f, c2)
                 m4, m5 = (int(host[0][k][b + 1] - host[0][k][b]) for k in range(2))
-                v += opcount.nyu_sparse_block_ops(2 * h, 2 * w, f // 2 + x_blocks[-3].shape[1], f // 4, m4, m5, False)
+                v += opcount.nyu_sparse_block_ops(2 * h, 2 * w, f // 2 + c3, f // 4, m4, m5, False)
                 m4, m5 = (int(host[1][k][b + 1] - host[1][k][b]) for k in range(2))
-                v += opcount.nyu_sparse_block_ops(4 * h, 4 * w, f // 4 + x_blocks[-4].shape[1], f // 8, m4, m5, True)
+                v += opcount.nyu_sparse_block_ops(4 * h, 4 * w, f // 4 + c4, f // 8, m4, m5, True)
                 per_sample.append(v)
-            out["total_ops"] = sum(per_sample)
+            res = {"total_ops": sum(per_sample)}
             if n > 1:
-                out["total_ops_per_sample"] = per_sample
+                res["total_ops_per_sample"] = per_sample
+            return res
+
+        return OpsFuture(counts, finish)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# API surface outside the hot path (SURVEY 8b lists them as constructible from NYUv2/model.py:47-64): the DenseDepth
+# baseline decoders and the 224-pixel wavelet variant.  They run on the differentiable cuDNN path (+ the native IDWT
+# through its autograd function); no native gather-GEMM engine is built for them.
+# ------------------------------------------------------------------------------------------------------------------
+class _BaselineDecoder(nn.Module):
+    """conv2 -> four UpSampleBlocks -> [x2 + conv5 + LeakyReLU(0.2)] -> conv3; zero padding everywhere."""
+
+    def _build(self, enc_features, decoder_width, is_depthwise, extra_stage):
+        f = int(enc_features[-1] * decoder_width)
+        self.conv2 = Conv3x3(enc_features[-1], f, padding="zero")
+        for k in range(1, 5):
+            setattr(self, "up%d" % k, UpSampleBlock(skip_input=f // 2 ** (k - 1) + enc_features[-1 - k],
+                                                    output_features=f // 2 ** k, padding="zero",
+                                                    is_depthwise=is_depthwise))
+        last = f // 16
+        if extra_stage:
+            self.conv5 = nn.Sequential(Conv3x3(f // 16, f // 32, is_depthwise=is_depthwise), nn.LeakyReLU(0.2))
+            last = f // 32
+        if is_depthwise:
+            self.conv3 = Conv3x3(last, 1, is_depthwise=True)
+        else:
+            self.conv3 = nn.Conv2d(last, 1, kernel_size=3, stride=1, padding=1, padding_mode="zeros")
+        if extra_stage:
+            self.upsample = nn.Upsample(scale_factor=2, mode="nearest")
+        self._extra_stage = extra_stage
+
+    def forward(self, features):
+        blocks = tuple(features)
+        if len(blocks) != 5:
+            raise ValueError("expected the five encoder blocks, fine to coarse")
+        x = self.conv2(blocks[4])
+        for k in range(1, 5):
+            x = getattr(self, "up%d" % k)(x, blocks[4 - k])
+        if self._extra_stage:
+            x = self.conv5(self.upsample(x))
+        return {("disp", 0): self.conv3(x)}
+
+
+class Decoder(_BaselineDecoder):
+    """DenseDepth baseline decoder (no wavelets).  [densedepth_decoder.py:15-47]"""
+
+    def __init__(self, enc_features=[96, 96, 192, 384, 2208], decoder_width=0.5, is_depthwise=False):
+        super().__init__()
+        self._build(enc_features, decoder_width, is_depthwise, extra_stage=False)
+
+
+class Decoder224(_BaselineDecoder):
+    """Baseline decoder for 224-pixel inputs: one more x2 + conv stage.  [densedepth_decoder.py:50-89]"""
+
+    def __init__(self, enc_features=[96, 96, 192, 384, 2208], decoder_width=0.5, is_depthwise=False):
+        super().__init__()
+        self._build(enc_features, decoder_width, is_depthwise, extra_stage=True)
+
+
+class DecoderWave224(nn.Module):
+    """Four-level wavelet decoder for 224-pixel inputs.  [densedepth_decoder.py:151-221]
+
+    Same state-dict names as the reference (conv2, up1..up4, wave1_ll, wave1..wave4, iwt / iwt_LL buffers).  Keeps the
+    reference's quirk of FLOOR-dividing ``("disp", 1)`` (:212)."""
+
+    def __init__(self, enc_features=[96, 96, 192, 384, 2208], decoder_width=0.5, dw_waveconv=False, dw_upconv=False):
+        super().__init__()
+        f = int(enc_features[-1] * decoder_width)
+        self.iwt = IDWT(wave="haar", mode="zero")
+        self.iwt_LL = IDWT(wave="haar", mode="zero")
+        self.conv2 = Conv3x3(enc_features[-1], f, padding="replicate")
+        self.up1 = UpSampleBlock(skip_input=f + enc_features[-2], output_features=f // 2, padding="reflection",
+                                 is_depthwise=dw_upconv)
+        self.wave1_ll = Conv3x3(f // 2, 1, padding="replicate")
+        self.wave1 = Conv3x3(f // 2, 3, padding="zero", is_depthwise=dw_waveconv)
+        for k in range(2, 5):
+            setattr(self, "up%d" % k, UpSampleBlock(skip_input=f // 2 ** (k - 1) + enc_features[-1 - k],
+                                                    output_features=f // 2 ** k, padding="reflection",
+                                                    is_depthwise=dw_upconv))
+            setattr(self, "wave%d" % k, Conv3x3(f // 2 ** k, 3, padding="zero", is_depthwise=dw_waveconv))
+        self.sigmoid = nn.Sigmoid()
+
+    def forward(self, x_blocks):
+        _need_cuda(x_blocks)
+        out = {}
+        x = self.up1(self.conv2(x_blocks[-1]), x_blocks[-2])
+        ll = (2 ** 4) * self.wave1_ll(x)
+        out[("wavelets", 3, "LL")] = ll
+        for k in range(1, 5):                                # level k emits scale 4 - k
+            s = 4 - k
+            if k > 1:
+                x = getattr(self, "up%d" % k)(x, x_blocks[-1 - k])
+            hcoef = (2 ** s) * getattr(self, "wave%d" % k)(x).unsqueeze(1)
+            for j, band in enumerate(("LH", "HL", "HH")):
+                out[("wavelets", s, band)] = hcoef[:, :, j]
+            ll = self.iwt((ll, [hcoef]))
+            out[("disp", s)] = ll // 2 if s == 1 else ll / (2 ** s)
         return out

@@ -28,37 +28,74 @@ def _dense(t, dtype=_f32):
 
 
 class _Scratch:
-    """Per-device scratch buffers for the range / compaction kernels."""
+    """Scratch buffers for the range / compaction / split-K kernels, one set per (device, stream).
+
+    Two decoders on different streams of one device must not share the self-cleaning range counters or the split-K
+    partial sums, so buffers are keyed by the stream they are used on.  A buffer that is outgrown is RETIRED, not
+    freed: a captured CUDA graph (graphs.py) holds raw addresses of the buffers that were current at capture time and
+    keeps replaying into them."""
 
     def __init__(self):
-        self.range_ws = {}
-        self.compact_ws = {}
-        self.splitk_ws = {}
+        self.bufs = {}
+        self.retired = []
+
+    @staticmethod
+    def _key(kind, device, slot=0):
+        return (kind, device.index if device.index is not None else torch.cuda.current_device(),
+                torch.cuda.current_stream(device).cuda_stream, slot)
+
+    def _get(self, key, device, nbytes, floor, zero):
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                self.retired.append(buf)
+            buf = (torch.zeros if zero else torch.empty)(max(nbytes, floor), dtype=_u8, device=device)
+            self.bufs[key] = buf
+        return buf
 
     def range(self, device, nbytes):
-        buf = self.range_ws.get(device)
-        if buf is None or buf.numel() < nbytes:
-            buf = torch.zeros(max(nbytes, 1 << 16), dtype=_u8, device=device)   # zeroed once; kernel keeps it zero
-            self.range_ws[device] = buf
-        return buf
+        return self._get(self._key("range", device), device, nbytes, 1 << 16, True)    # zeroed once; kernel keeps it zero
 
     def splitk(self, device, nbytes):
-        buf = self.splitk_ws.get(device)
-        if buf is None or buf.numel() * 4 < nbytes:
-            buf = torch.empty((nbytes + 3) // 4, dtype=_f32, device=device)
-            self.splitk_ws[device] = buf
-        return buf
+        return self._get(self._key("splitk", device), device, (nbytes + 15) // 16 * 16, 16, False).view(_f32)
 
     def compact(self, device, nbytes, slot=0):
-        """slot: compactions that may run concurrently (different streams) need different workspaces."""
-        buf = self.compact_ws.get((device, slot))
-        if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(nbytes, 1 << 16), dtype=_u8, device=device)
-            self.compact_ws[(device, slot)] = buf
-        return buf
+        """slot: compactions that may run concurrently need different workspaces (side streams have their own key
+        anyway; the slot also separates them when the caller serialises them on one stream)."""
+        return self._get(self._key("compact", device, slot), device, nbytes, 1 << 16, False)
 
 
 _scratch = _Scratch()
+
+
+def _on_device(fn):
+    """Run a wrapper with its tensors' device current.
+
+    libwmd launches on the CUDA *current* device (it caches per-device attributes by cudaGetDevice()) and on the
+    stream handed in, so both must belong to the device that owns the buffers.  The first CUDA tensor among the
+    arguments decides; a decoder living on cuda:1 therefore works while cuda:0 is the process-wide current device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None:
+            for a in kwargs.values():
+                if torch.is_tensor(a) and a.is_cuda:
+                    dev = a.device
+                    break
+            if dev is None and isinstance(kwargs.get("device"), torch.device) and kwargs["device"].type == "cuda":
+                dev = kwargs["device"]
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
 
 
 class Profiler:
@@ -102,6 +139,7 @@ class _prof:
 
 
 # --------------------------------------------------------------------------- Haar
+@_on_device
 def idwt_haar(ll, hf, disp_scale=None, clamp01=False):
     """ll (N,C,H,W), hf (N,C,3,H,W) -> out (N,C,2H,2W) [, disp = clamp?(out*disp_scale)]."""
     lib = _lib.load()
@@ -121,6 +159,7 @@ def idwt_haar(ll, hf, disp_scale=None, clamp01=False):
     return (out, disp) if disp_scale is not None else out
 
 
+@_on_device
 def idwt_bilinear(ll, hf, size, disp_scale=1.0, clamp01=False, align_corners=False):
     """Fused IDWT -> disp = [clamp](out*disp_scale) -> bilinear resize to `size` (F.interpolate semantics)."""
     lib = _lib.load()
@@ -136,6 +175,7 @@ def idwt_bilinear(ll, hf, size, disp_scale=1.0, clamp01=False, align_corners=Fal
     return full
 
 
+@_on_device
 def dwt_haar(x):
     """x (N,C,H,W) even H,W -> ll (N,C,H/2,W/2), hf (N,C,3,H/2,W/2)."""
     lib = _lib.load()
@@ -152,6 +192,7 @@ def dwt_haar(x):
 
 
 # --------------------------------------------------------------------------- masks
+@_on_device
 def range_thresh(x, ratio, return_minmax=False):
     """Per-sample (max - min) * ratio over everything but dim 0 -> (N,) fp32 on device."""
     lib = _lib.load()
@@ -169,6 +210,7 @@ def range_thresh(x, ratio, return_minmax=False):
     return (thresh, mm) if return_minmax else thresh
 
 
+@_on_device
 def level_masks(yh, thresh, n=None, h=None, w=None, device=None, want=("S0", "S1", "S2", "S3", "S4", "S5")):
     """yh (N,3,H,W) or (N,1,3,H,W), thresh (N,) or None (all ones; then pass n,h,w,device).
 
@@ -195,6 +237,7 @@ def level_masks(yh, thresh, n=None, h=None, w=None, device=None, want=("S0", "S1
     return out
 
 
+@_on_device
 def compact(mask, want_idxmap=True, want_pixels=True, stream=None, ws_slot=0):
     """mask uint8 (N,1,H,W) or (N,H,W) -> idxmap int32 (N,H,W) | None, pixels int32 (N*H*W,) | None, offsets int32 (N+1,).
 
@@ -228,6 +271,7 @@ def compact(mask, want_idxmap=True, want_pixels=True, stream=None, ws_slot=0):
     return (idxmap, pixels, offsets), done
 
 
+@_on_device
 def gate_map(gate, idxmap=None):
     """int32 map: gate ? (idxmap or linear index) : -1, shaped like gate without the channel dim."""
     lib = _lib.load()
@@ -244,6 +288,7 @@ def pad4(c):
     return (int(c) + 3) // 4 * 4
 
 
+@_on_device
 def nchw_to_rows(x, ld=None, stream=None, gate=None):
     """(N,C,H,W) -> rows (N*H*W, ld) pixel-major.  Zero-copy when x is channels_last and C % 4 == 0.
 
@@ -304,6 +349,7 @@ def _pm_count(gate):
     return gate.sum()
 
 
+@_on_device
 def rows_to_nchw(rows, n, c, h, w):
     lib = _lib.load()
     rows = _dense(rows)
@@ -314,6 +360,7 @@ def rows_to_nchw(rows, n, c, h, w):
     return out
 
 
+@_on_device
 def gather_rows(x_nchw, pixels, count, max_rows=None, ld=None):
     """rows[m] = x[n, :, y, x] at the listed pixels (pixels/count None = every pixel)."""
     lib = _lib.load()
@@ -328,6 +375,7 @@ def gather_rows(x_nchw, pixels, count, max_rows=None, ld=None):
     return rows
 
 
+@_on_device
 def scatter_rows(rows, c, pixels, count, n, h, w, max_rows=None, out=None):
     """Dense (N,C,H,W), zero except at the listed pixels where it takes rows[m, :c]."""
     lib = _lib.load()
@@ -379,6 +427,7 @@ def default_conv_kind():
     return os.environ.get("WMD_CONV_IMPL", "auto")
 
 
+@_on_device
 def pack_weight(weight, c1=0, kind=None):
     """(Cout,Cin,k,k) conv weight -> PackedW.  c1 = trailing input channels that come from gather source 1.
 
@@ -406,6 +455,7 @@ def pack_weight(weight, c1=0, kind=None):
 
 
 # --------------------------------------------------------------------------- conv
+@_on_device
 def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act=ACT_NONE, act_param=0.0,
               map0=None, shift0=0, x1=None, c1=0, gate=None, pixels=None, count=None, max_rows=None, out=None,
               m_in0=None, m_in1=None, splits=None):
@@ -458,6 +508,7 @@ def head_mlp_supported(c, n1):
     return bool(_lib.load().wmd_head_mlp_supported(int(c), int(n1)))
 
 
+@_on_device
 def pack_head_mlp(w1, b1, wz):
     """(n1, c, 1, 1) 1x1 weight, (n1,) bias, (nz, n1, 1, 1) tap-product weight -> packed image for head_mlp."""
     lib = _lib.load()
@@ -475,6 +526,7 @@ def pack_head_mlp(w1, b1, wz):
     return packed
 
 
+@_on_device
 def head_mlp(x, c, packed, n1, slope=0.1, count=None, max_rows=None, nz=54):
     """z (max_rows, 56) = Wz . lrelu(W1 . x + b1) on pixel-major rows x (R, ld >= c); see wmd_head_mlp_f32."""
     lib = _lib.load()
@@ -487,6 +539,7 @@ def head_mlp(x, c, packed, n1, slope=0.1, count=None, max_rows=None, nz=54):
     return z
 
 
+@_on_device
 def head_conv3x3(t, c, off_a, wa, ba, n, h, w, cout, scale=1.0, act=ACT_NONE, pad=PAD_REFLECT, off_b=-1, wb=None,
                  bb=None, idxmap=None, pixels=None, count=None, max_rows=None, out=None):
     """3x3 stage of the coefficient heads -> dense (N,cout,H,W); see wmd_head_conv3x3_f32.
@@ -512,6 +565,7 @@ def head_conv3x3(t, c, off_a, wa, ba, n, h, w, cout, scale=1.0, act=ACT_NONE, pa
     return out
 
 
+@_on_device
 def pack_head_weight(weight):
     """(cout<=4, c, 3, 3) -> (9*c, cout) contiguous, the layout wmd_head_conv3x3_f32 stages in shared memory."""
     lib = _lib.load()
@@ -538,6 +592,7 @@ def head_tap_weight(w_list, offsets, ctot):
     return out.reshape(9 * g_total, ctot, 1, 1)
 
 
+@_on_device
 def head_gather(z, groups, bias, n, h, w, cout, scale=1.0, act=ACT_NONE, dual=False, pad=PAD_REFLECT, idxmap=None,
                 pixels=None, count=None, max_rows=None, out=None, col0=0):
     """Sum the nine per-tap products of z (rows x >= 9*groups) around every output pixel -> dense (N,cout,H,W).

@@ -24,6 +24,25 @@ RESNET18_CH = (64, 64, 128, 256, 512)
 RESNET50_CH = (64, 256, 512, 1024, 2048)
 DENSENET161_CH = (96, 96, 192, 384, 2208)
 
+# The synthetic workload bench.py measures and the full-size parity tests check (one definition for both):
+# seeded PyTorch-default init with high-pass coefficient heads x4 and blocky features, cell 16 px.
+KITTI_HEAD_KEYS = ["decoder.%d.2.conv." % k for k in (3, 4, 7, 8, 11, 12, 15, 16)]   # +/- coefficient heads' 3x3 stage
+BENCH_SYNTH = dict(param_seed=7, feat_seed=1000, cell=16, texture=0.01, head_gain=4.0)
+
+
+def bench_kitti_params(module_or_shapes):
+    """Bench weights: loads them into a module (returns the state dict) or builds the dict from {name: shape}."""
+    gains = {k: BENCH_SYNTH["head_gain"] for k in KITTI_HEAD_KEYS}
+    if isinstance(module_or_shapes, dict):
+        return random_state_dict(module_or_shapes, BENCH_SYNTH["param_seed"], gains, KITTI_HEAD_KEYS)
+    return load_random(module_or_shapes, seed=BENCH_SYNTH["param_seed"], gains=gains, highpass=KITTI_HEAD_KEYS)
+
+
+def bench_kitti_features(n, height, width, ch, first_sample=0, pin=False):
+    """Bench features of samples first_sample .. first_sample+n-1 (sample k of any batch is the same tensor)."""
+    return blocky_features(kitti_feature_shapes(n, height, width, ch), seed=BENCH_SYNTH["feat_seed"] + first_sample,
+                           cell=BENCH_SYNTH["cell"], texture=BENCH_SYNTH["texture"], pin=pin)
+
 
 def random_state_dict(shapes, seed, gains=None, highpass=None):
     """shapes: ordered {name: shape}; names ending in '.weight' / '.bias' are filled, others skipped.
