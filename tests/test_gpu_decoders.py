@@ -501,3 +501,27 @@ def test_decoder_on_a_non_current_device():
     for s in range(4):
         assert torch.equal(got[("disp", s)].cpu(), want[("disp", s)].cpu())
     assert got["total_ops"] == want["total_ops"]
+
+
+def test_npy_coefficient_dumps_as_test_simple_writes_them(tmp_path):
+    """KITTI/test_simple.py:154-164 dumps, per scale, an (H_s, W_s, 4) float64 array [LL, LH, HL, HH] with np.save
+    (evaluate_depth.py:231-235 does the same for the sparse decoder).  Same procedure on the native outputs and on the
+    reference's golden outputs; the files must agree."""
+    want, meta = load_golden("kitti_tiny_dense")
+    mod, _ = _kitti(kd.DepthWaveProgressiveDecoder, meta)
+    with torch.no_grad():
+        outputs = mod(kitti_features(meta, DEV))
+    coeffs = ["LL", "LH", "HL", "HH"]
+    fh, fw = meta["height"], meta["width"]
+    for scale in range(4):
+        mine = np.zeros((fh // (2 ** (scale + 1)), fw // (2 ** (scale + 1)), 4))
+        ref = np.zeros_like(mine)
+        for j in range(4):
+            mine[..., j] = outputs[("wavelets", scale, coeffs[j])].cpu()[0, 0].numpy()
+            ref[..., j] = want["wavelets_%d_%s" % (scale, coeffs[j])][0, 0]
+        np.save(tmp_path / ("x_scale_%d_wavelets.npy" % scale), mine)
+        back = np.load(tmp_path / ("x_scale_%d_wavelets.npy" % scale))
+        assert back.dtype == np.float64 and back.shape == ref.shape
+        assert rel_err(back, ref) <= REL_TOL
+    np.save(tmp_path / "x_disp.npy", outputs[("disp", 0)].cpu().numpy())
+    assert rel_err(np.load(tmp_path / "x_disp.npy"), want["disp_0"]) <= REL_TOL

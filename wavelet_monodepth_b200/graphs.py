@@ -14,6 +14,8 @@ same tensors, which is how a CUDA-graphed encoder behaves anyway.  Scratch buffe
 ops._scratch (buffers are retired, never freed) and, being allocated on the capture stream, are not shared with eager
 calls on other streams.
 """
+import gc
+
 import torch
 
 from . import _lib
@@ -36,23 +38,34 @@ class GraphedSparseDecoder:
         self.thresh_ratio = float(thresh_ratio)
         if isinstance(decoder, SparseDepthWaveProgressiveDecoder):
             self.sparse_levels = decoder._sparse_levels(sparse_scales)
-            self._run = lambda: decoder._native_forward(self.features, self.thresh_ratio, self.sparse_levels, with_masks=True)
-            self._future = lambda: decoder.ops_future(self._counts, self.features, self.sparse_levels)
         elif isinstance(decoder, SparseDecoderWave):
-            self._run = lambda: decoder._native_forward(self.features, self.thresh_ratio, sparse=True)
-            self._future = lambda: decoder.ops_future(self._counts, self.features)
+            self.sparse_levels = None
         else:
             raise WmdError("GraphedSparseDecoder wraps a SparseDepthWaveProgressiveDecoder or a SparseDecoderWave")
         self.device = next(f.device for f in self.features if f.is_cuda)
         with torch.cuda.device(self.device):
             for _ in range(max(1, warmup)):                 # packs the weights, sizes the scratch buffers
                 self._run()
+            # Destroying a CUDA graph is not permitted while ANY stream of the process is capturing (global capture
+            # mode): it would invalidate this capture.  Make sure no dead graph object is waiting for the cycle
+            # collector (this class itself holds no reference cycles, so `del graph` frees it at once).
+            gc.collect()
             torch.cuda.synchronize()
             l0 = _lib.launch_count()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._out, self._counts = self._run()
             self.launches = _lib.launch_count() - l0        # libwmd kernels per replay
+
+    def _run(self):
+        if self.sparse_levels is None:
+            return self.decoder._native_forward(self.features, self.thresh_ratio, sparse=True)
+        return self.decoder._native_forward(self.features, self.thresh_ratio, self.sparse_levels, with_masks=True)
+
+    def _future(self):
+        if self.sparse_levels is None:
+            return self.decoder.ops_future(self._counts, self.features)
+        return self.decoder.ops_future(self._counts, self.features, self.sparse_levels)
 
     def bound_to(self, features):
         """True if `features` are the tensors this graph reads."""
