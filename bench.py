@@ -160,6 +160,11 @@ def account(name, info):
         m = min(_as_int(info["count"], n * h * w), info["max_rows"])
         heads = 2 if info["dual"] else 1
         return 4 * (m * c * heads + m * cout) + 4 * heads * (9 * c * cout + cout), 2 * 9 * c * cout * m * heads
+    if name == "head_idwt":
+        px = info["n"] * info["h"] * info["w"]
+        m = int(info["mask"].sum().item()) if info["mask"] is not None else px
+        # ll + mask in, yh + reconstruction + disp out (+ two epilogue planes), 9 x 6 tap products per active pixel
+        return px * (4 + (1 if info["mask"] is not None else 0) + 12 + 16 + 16 + (32 if info["epi"] else 0)) + m * 9 * 24, 9 * 6 * m + 14 * px
     if name == "idwt_haar":
         px = info["n"] * info["c"] * info["h"] * info["w"]
         return (32 + (16 if info["disp"] else 0)) * px, 14 * px

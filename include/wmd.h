@@ -206,6 +206,11 @@ int wmd_conv_rows_tc_f32(const wmd_conv_desc* d, wmd_stream_t stream);
  * together; only remainder tiles cut by a range boundary (<= 8 segments) go through the workspace + fixed-order
  * reduce pass.  Its workspace size does not depend on the layer (SMs x 8 x 256 x 128 floats). */
 size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits);
+/* 3x3 layers gather the A operand once per (channel chunk, dy) and feed the three dx taps from that one shared-memory
+ * stage through a per-tile slot table (sparse_conv3x3's nine shifted selections, KITTI/layers.py:445-453, read almost the
+ * same rows).  On by default; wmd_conv_tc_set_shared_taps(0) restores one gather per tap (A/B measurements, tests:
+ * both forms produce identical bits).  on < 0 only queries.  Returns the previous setting.  Process-wide. */
+int wmd_conv_tc_set_shared_taps(int on);
 int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* d, int splits, void* ws, size_t ws_bytes, wmd_stream_t stream);
 
 /* ---------------------------------------------------------------- coefficient heads (few output channels)
@@ -240,6 +245,52 @@ int wmd_head_conv3x3_f32(const wmd_head_desc* d, wmd_stream_t stream);
 int wmd_head_gather_f32(const float* z, int ldz, int groups, const int32_t* map, const float* bias, float scale, int act,
                         int dual, int pad_mode, const int32_t* pixels, const int32_t* count, int max_rows, float* out,
                         int cout, int N, int H, int W, wmd_stream_t stream);
+
+/* ---------------------------------------------------------------- fused tail of a decoder level
+ * One kernel for:  factored 3x3 stage of the +/- coefficient heads (get_coefficients / get_sparse_coefficients,
+ * depth_decoder.py:126-136,242-290: yh = 2^(i-1) (sigmoid(.) - sigmoid(.)), zero outside the wavelet mask)
+ *                  -> pytorch_wavelets.DWTInverse (depth_decoder.py:164,372,416)
+ *                  -> disp = clamp(yl / 2^(i-1), 0, 1) (depth_decoder.py:166)
+ *                  -> the consumer's epilogue of ("disp", 0): disp_to_depth (KITTI/layers.py:16-25) or depth / 100
+ *                     + clamp (NYUv2/utils.py:219,229)
+ *                  -> thresh = (max - min)(yl) * ratio of the NEXT level's masks (depth_decoder.py:308), per sample.
+ * z: rows of tap products from wmd_head_mlp_f32 / the tap-product GEMM, 54 floats [tap][+LH,+HL,+HH,-LH,-HL,-HH] from
+ * z[0] (pass z + col0 for a column offset), row of pixel q = map[q] (map == NULL: q), pixels with mask == 0 (mask != NULL)
+ * get zero coefficients.  yh (N,3,H,W) is written once (an output of the decoder) and not read back; out / disp are
+ * (N,1,2H,2W).  ll / mask rows of a tile are staged by TMA bulk copies when W % 16 == 0.  Results are bit-identical to
+ * wmd_head_gather_f32 + wmd_idwt_haar_f32 + wmd_range_thresh_f32.  thresh == NULL skips the range reduction (then ws may
+ * be NULL); otherwise ws needs wmd_head_idwt_ws_bytes() bytes whose first 64 KiB are zero before the first use (the kernel
+ * leaves them zeroed, like wmd_range_thresh_f32). */
+enum { WMD_EPI_NONE = 0, WMD_EPI_DISP_TO_DEPTH = 1, WMD_EPI_DIV_CLAMP = 2 };
+typedef struct wmd_head_idwt_desc {
+  int32_t N, H, W;           /* coefficient grid of the level */
+  const float* z;            /* tap-product rows [*][ldz] */
+  int32_t ldz;
+  const int32_t* map;        /* (N,H,W) row of a pixel in z, -1 = none; NULL = linear index */
+  const uint8_t* mask;       /* (N,H,W) wavelet mask (S5) or NULL = every pixel */
+  const float* bias;         /* [6]: + head's 3 biases then - head's, or NULL */
+  float scale;               /* 2^(i-1) */
+  int32_t pad_mode;          /* WMD_PAD_* of the heads' 3x3 stage */
+  const float* ll;           /* (N,1,H,W) */
+  float* yh;                 /* (N,3,H,W) */
+  float* out;                /* (N,1,2H,2W) reconstruction */
+  float* disp;               /* (N,1,2H,2W) = [clamp01](out * disp_scale), or NULL */
+  float disp_scale;
+  int32_t clamp01;
+  int32_t epi_mode;          /* WMD_EPI_*: DISP_TO_DEPTH: epi_out0 = epi_a + epi_b * disp, epi_out1 = 1 / epi_out0 (nullable);
+                                DIV_CLAMP: epi_out0 = out / epi_a, clamped to [epi_lo, epi_hi] if epi_b != 0 */
+  float epi_a, epi_b, epi_lo, epi_hi;
+  float* epi_out0;
+  float* epi_out1;
+  float* thresh;             /* (N) (max - min)(out_n) * thresh_ratio, or NULL */
+  float thresh_ratio;
+} wmd_head_idwt_desc;
+/* The plain IDWT with the same consumer epilogue (NYU decoders: the last level's reconstruction IS ("disp", 0)). */
+int wmd_idwt_haar_epi_f32(const float* ll, const float* hf, float* out, float* disp, float disp_scale, int clamp01,
+                          int epi_mode, float epi_a, float epi_b, float epi_lo, float epi_hi, float* epi_out0,
+                          float* epi_out1, int N, int C, int H, int W, wmd_stream_t stream);
+size_t wmd_head_idwt_ws_bytes(int N, int H, int W);
+int wmd_head_idwt_f32(const wmd_head_idwt_desc* d, void* ws, size_t ws_bytes, wmd_stream_t stream);
 
 #ifdef __cplusplus
 }

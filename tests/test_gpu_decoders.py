@@ -525,3 +525,45 @@ def test_npy_coefficient_dumps_as_test_simple_writes_them(tmp_path):
         assert rel_err(back, ref) <= REL_TOL
     np.save(tmp_path / "x_disp.npy", outputs[("disp", 0)].cpu().numpy())
     assert rel_err(np.load(tmp_path / "x_disp.npy"), want["disp_0"]) <= REL_TOL
+
+
+def test_fused_level_tail_is_bit_identical_to_the_three_kernel_chain_and_epilogue_matches_disp_to_depth():
+    """fused_tail: head gather-sum -> yh -> IDWT -> disp -> next threshold in one kernel (wmd_head_idwt_f32) must equal the
+    head_gather + idwt_haar + range_thresh chain bit for bit (same summation order), on sparse, masked-dense and dense
+    levels, TMA-staged (W % 16 == 0) and plain staging; depth_range adds disp_to_depth(("disp", 0)) (KITTI/layers.py:16-25)."""
+    for ch, hw in ((synth.RESNET18_CH, (192, 640)), (synth.RESNET18_CH, (128, 256))):      # widths 40.. (plain) / 16.. (TMA)
+        mod, dense, feats = _full_kitti(ch, 3, *hw)
+        for scales in ([1, 2, 3], [1]):
+            mod.fused_tail = False
+            want = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in mod(feats, 0.05, scales).items()}
+            mod.fused_tail = True
+            got = mod(feats, 0.05, scales)
+            assert set(got) == set(want)
+            for k, v in want.items():
+                assert (torch.equal(got[k], v) if torch.is_tensor(v) else got[k] == v), (hw, scales, key_str(k))
+        dense.fused_tail = False
+        with torch.no_grad():
+            want = {k: v.clone() for k, v in dense(feats).items()}
+            dense.fused_tail = True
+            got = dense(feats)
+        for k, v in want.items():
+            assert torch.equal(got[k], v), (hw, "dense", key_str(k))
+        mod.depth_range = (0.1, 100.0)
+        got = mod(feats, 0.05)
+        disp = got[("disp", 0)]
+        min_disp, max_disp = 1 / 100.0, 1 / 0.1                      # the reference's arithmetic, on the GPU by torch
+        scaled = min_disp + (max_disp - min_disp) * disp
+        assert torch.equal(got[("scaled_disp", 0)], scaled)
+        assert rel_err(got[("depth", 0)], 1 / scaled) <= 1e-6
+        mod.depth_range = None
+
+
+def test_nyu_consumer_epilogue_depth_div_clamp():
+    """NYUv2/utils.py:219,229: pred = clamp(outputs[("disp", 0)] / 100, 0.4, 10) - fused into the last IDWT."""
+    yl = torch.rand(2, 1, 24, 32, device=DEV) * 800
+    yh = (torch.rand(2, 1, 3, 24, 32, device=DEV) - 0.5) * 100
+    out, depth = ops.idwt_haar(yl, yh, epilogue=("div_clamp", 100.0, 0.4, 10.0))
+    assert torch.equal(out, ops.idwt_haar(yl, yh))
+    assert torch.equal(depth, torch.clamp(out / 100, min=0.4, max=10))
+    _, depth2 = ops.idwt_haar(yl, yh, epilogue=("div_clamp", 100.0, None, None))
+    assert torch.equal(depth2, out / 100)

@@ -412,3 +412,68 @@ def test_fused_head_mlp_vs_torch(c, rows, count):
         t2 = ops.conv_rows(x.to(DEV), c, wp, b1.to(DEV), n1, 1, 1, rows, taps=1, act=ACT_LRELU, act_param=0.1)
         z2 = ops.conv_rows(t2, n1, ops.pack_weight(wz.to(DEV), kind="simt"), None, nz, 1, 1, rows, taps=1)
         assert rel_err(z[:m, :nz], z2[:m, :nz]) <= 1e-5
+
+
+def _blob_mask(n, h, w, p, seed, grow):
+    """uint8 (n,1,h,w): random seeds dilated `grow` times by a 3x3 window - clustered like the decoder's dilated sets."""
+    rs = np.random.RandomState(seed)
+    m = torch.from_numpy((rs.uniform(size=(n, 1, h, w)) < p).astype(np.float32))
+    for _ in range(grow):
+        m = F.max_pool2d(m, 3, 1, 1)
+    return m.to(torch.uint8)
+
+
+@pytest.mark.parametrize("case", ["dense_two_sources", "blobs_two_sources_balanced", "blobs_one_source", "isolated_pixels_fallback",
+                                  "thin_n32", "wide_n128"])
+def test_shared_tap_gather_is_bit_identical_to_per_tap_gather(case):
+    """conv_rows_tc<N, SH>: one raw-stage fill per (chunk, dy) feeding the three dx taps through the slot table must give
+    the bits of the one-gather-per-tap form (same MMAs, same order) - dense grids, clustered active lists (extras at
+    run ends), isolated pixels (extras overflow -> per-chunk fills), stream-K cuts that start mid-group, all N tiles."""
+    from wavelet_monodepth_b200 import _lib
+    lib = _lib.load()
+    cfg = {
+        "dense_two_sources": dict(n=2, h=40, w=64, c0=64, c1=96, cout=64, p=None, grow=0, pad=PAD_REFLECT),
+        "blobs_two_sources_balanced": dict(n=3, h=48, w=96, c0=256, c1=64, cout=64, p=0.02, grow=2, pad=PAD_REFLECT),
+        "blobs_one_source": dict(n=4, h=64, w=80, c0=128, c1=0, cout=64, p=0.03, grow=2, pad=PAD_ZERO),
+        "isolated_pixels_fallback": dict(n=2, h=48, w=64, c0=64, c1=32, cout=48, p=0.35, grow=0, pad=PAD_REPLICATE),
+        "thin_n32": dict(n=2, h=64, w=128, c0=32, c1=64, cout=32, p=0.04, grow=1, pad=PAD_REFLECT),
+        "wide_n128": dict(n=2, h=24, w=40, c0=160, c1=96, cout=128, p=0.05, grow=2, pad=PAD_REFLECT),
+    }[case]
+    n, h, w, c0, c1, cout = (cfg[k] for k in ("n", "h", "w", "c0", "c1", "cout"))
+    wt, b = rnd(cout, c0 + c1, 3, 3, seed=70, lo=-0.1, hi=0.1), rnd(cout, seed=71)
+    wp = ops.pack_weight(wt.to(DEV), c1, kind="tc")
+    kw = dict(pad=cfg["pad"], act=ACT_ELU)
+    if c1:                                               # upconv(i,1) form: low-res source through map + shift, skip source gated
+        lo_rows = rnd(n * (h // 2) * (w // 2), c0, seed=72).to(DEV)
+        skip = rnd(n * h * w, c1, seed=73).to(DEV)
+        kw.update(shift0=1, x1=skip, c1=c1)
+    else:
+        lo_rows = rnd(n * h * w, c0, seed=72).to(DEV)
+    if cfg["p"] is not None:
+        out_mask = _blob_mask(n, h, w, cfg["p"], 74, cfg["grow"]).to(DEV)
+        _, pixels, offsets = ops.compact(out_mask, want_idxmap=False)
+        kw.update(pixels=pixels, count=offsets[n:])
+        if c1:
+            gate = _blob_mask(n, h, w, cfg["p"], 74, cfg["grow"] + 1).to(DEV)          # superset of the outputs
+            lo_mask = _blob_mask(n, h // 2, w // 2, 0.5, 75, 1).to(DEV)
+            map0, _, _ = ops.compact(lo_mask, want_pixels=False)
+            kw.update(gate=gate, map0=map0)
+        else:
+            in_mask = _blob_mask(n, h, w, cfg["p"], 74, max(cfg["grow"] - 1, 0)).to(DEV)
+            map0, _, _ = ops.compact(in_mask, want_pixels=False)
+            kw.update(map0=map0)
+        assert int(offsets[n]) > 3 * 256                # several tiles
+    outs = []
+    was = lib.wmd_conv_tc_set_shared_taps(-1)
+    try:
+        for sh in (0, 1):
+            lib.wmd_conv_tc_set_shared_taps(sh)
+            for _ in range(2):                           # twice: deterministic
+                outs.append(ops.conv_rows(lo_rows, c0, wp, b.to(DEV), cout, n, h, w, **kw).clone())
+            torch.cuda.synchronize()
+    finally:
+        lib.wmd_conv_tc_set_shared_taps(was)
+    rows = int(kw["count"][0]) if "count" in kw else n * h * w
+    for o in outs[1:]:
+        assert torch.equal(o[:rows, :cout], outs[0][:rows, :cout])
+    assert float(outs[0][:rows].abs().max()) > 0

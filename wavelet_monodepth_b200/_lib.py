@@ -48,6 +48,23 @@ class HeadDesc(Structure):
     ]
 
 
+class HeadIdwtDesc(Structure):
+    """struct wmd_head_idwt_desc (include/wmd.h)."""
+    _fields_ = [
+        ("N", c_int32), ("H", c_int32), ("W", c_int32),
+        ("z", c_void_p), ("ldz", c_int32),
+        ("map", c_void_p), ("mask", c_void_p), ("bias", c_void_p),
+        ("scale", c_float), ("pad_mode", c_int32),
+        ("ll", c_void_p), ("yh", c_void_p), ("out", c_void_p), ("disp", c_void_p),
+        ("disp_scale", c_float), ("clamp01", c_int32),
+        ("epi_mode", c_int32), ("epi_a", c_float), ("epi_b", c_float), ("epi_lo", c_float), ("epi_hi", c_float),
+        ("epi_out0", c_void_p), ("epi_out1", c_void_p),
+        ("thresh", c_void_p), ("thresh_ratio", c_float),
+    ]
+
+
+EPI_NONE, EPI_DISP_TO_DEPTH, EPI_DIV_CLAMP = 0, 1, 2
+
 # name -> (restype, argtypes); must list every symbol include/wmd.h declares (tests/test_abi.py checks)
 SIGNATURES = {
     "wmd_version": (c_int, []),
@@ -56,6 +73,8 @@ SIGNATURES = {
     "wmd_launch_count": (c_longlong, []),
     "wmd_idwt_haar_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int,
                                   c_int, c_void_p]),
+    "wmd_idwt_haar_epi_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_float, c_float, c_float,
+                                      c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "wmd_idwt_bilinear_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_void_p]),
     "wmd_dwt_haar_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -83,12 +102,15 @@ SIGNATURES = {
                                  c_void_p]),
     "wmd_conv_rows_f32": (c_int, [POINTER(ConvDesc), c_void_p]),
     "wmd_conv_tc_tile_n": (c_int, [c_int]),
+    "wmd_conv_tc_set_shared_taps": (c_int, [c_int]),
     "wmd_conv_tc_weight_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "wmd_pack_conv_weight_tc_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "wmd_conv_rows_tc_f32": (c_int, [POINTER(ConvDesc), c_void_p]),
     "wmd_conv_tc_splitk_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wmd_conv_rows_tc_splitk_f32": (c_int, [POINTER(ConvDesc), c_int, c_void_p, c_size_t, c_void_p]),
     "wmd_head_conv3x3_f32": (c_int, [POINTER(HeadDesc), c_void_p]),
+    "wmd_head_idwt_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "wmd_head_idwt_f32": (c_int, [POINTER(HeadIdwtDesc), c_void_p, c_size_t, c_void_p]),
     "wmd_head_gather_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }

@@ -28,6 +28,14 @@
 // What bounds it (scripts/tc_trace.py, scripts/bench_cu/*): shared-memory wavefronts.  Per chunk at N=128 the MMAs read
 // B 24 x 4 KB (768 wavefronts), B lands (256), raw A lands (256) and is read back (256): ~1540 clk against ~1620 clk of
 // tensor-pipe work.  The earlier cp.async gather cost ~640 wavefronts per chunk on top and serialised with the split.
+// Shared-tap gather (SH = true, every 3x3 layer): the three dx taps of a (channel chunk, dy) read almost the same source
+// rows - tap dx of tile row r is tap 0 of row r + dx whenever the two output pixels are neighbours in the active list.
+// One raw stage fill per (chunk, dy) therefore serves THREE chunks: slots 0..255 hold the dx = 0 sources of the tile's
+// rows, slots 256.. the few "extra" rows that no centre tap fetches (run ends, list gaps); a per-tile slot table
+// (uint16 per (source, dy, side, row)) tells the split warps which slot feeds each row of the dx = +-1 chunks.  The
+// L2->SM traffic of the A operand and the TMA gather4 count drop ~3x (measured intake limit: ~45 B/clk/SM, at which
+// re-gathering every tap bounds all layers with N <= 64).  A tile whose extras overflow (isolated pixels: > 128 per
+// (source, dy)) falls back to one fill per chunk with identity slots - same code, group size 1.
 // TMEM map (512 columns): [0,2N) accumulators (half h at h*N), [256,512) A operand: stage s, half h at
 // 256 + s*128 + h*64, hi in the first 32 columns, lo in the next 32.
 #include <cuda.h>   // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
@@ -38,26 +46,44 @@ namespace wmd {
 
 constexpr int TC_BM = 256;                      // rows per CTA tile = 2 UMMA halves of 128
 constexpr int TC_BK = 32;                       // floats per chunk = one 128-byte swizzle-atom row
-constexpr int TC_THREADS = 512;                 // 16 warps: 8 split + 6 gather + 2 issuers; all drain (lane quarter w&3, half (w>>2)&1, cols w>>3)
+constexpr int TC_THREADS = 512;                 // 16 warps: 8 split + 5 gather + 1 weight loader + 2 issuers; all drain (lane quarter w&3, half (w>>2)&1, cols w>>3)
 constexpr int TC_SPLIT_WARPS = 8;               // warps 0-7: warp w owns tile rows (w>>2)*128 + (w&3)*32 + lane (its TMEM lane quarter)
-constexpr int TC_GATHER_WARPS = 6;              // warps 8-13
+constexpr int TC_GATHER_WARPS = 5;              // warps 8-12
+constexpr int TC_WLOAD_WARP = 13;               // warp 13: weight (B) loader - keeps the issuers' loop free of the stage-reuse wait
 constexpr int TC_ISSUERS = 2;                   // warps 14-15: one per M half, each the only writer of its accumulator
 constexpr int TC_A_STAGES = 3;                  // raw A tiles in shared memory (two gathers in flight + one being split)
-constexpr int TC_T_STAGES = 2;                  // split A stages in tensor memory
-constexpr int TC_B_STAGES = 3;                  // [Bhi | Blo] images in shared memory
+constexpr int TC_T_STAGES_MAX = 3;              // split A stages in tensor memory: 2 (N = 128) or 3 (N <= 64), see TcCfg
+constexpr int TC_B_STAGES_MAX = 4;              // [Bhi | Blo] images in shared memory: 3 (N = 128) or 4 (N <= 64)
 constexpr int TC_A_TILE = TC_BM * TC_BK * 4;    // 32 KB raw fp32
 constexpr int TC_TABLES = 2 * 9 * TC_BM * 4;
 constexpr int TC_TMEM_COLS = 512;
+// shared-tap gather (SH): 2 raw stages of 256 tile rows + 128 extra rows
+constexpr int TC_SH_STAGES = 2;
+constexpr int TC_SH_EXTRA = 128;
+constexpr int TC_SH_ROWS = TC_BM + TC_SH_EXTRA;
+constexpr int TC_SH_TILE = TC_SH_ROWS * 128;     // 48 KB
+constexpr int TC_SH_TABLES = 2 * 3 * TC_SH_EXTRA * 4 /* extra source rows */ + 2 * 3 * 2 * TC_BM * 2 /* slots */ + 64 /* counters */;
+constexpr uint16_t kZeroSlot = 0xFFFFu;          // slot-table entry of a tap that reads nothing (inactive / padded source)
 
 // Per N-tile configuration.  Accumulators: M half h at TMEM column h*BN; each is written by exactly one issuer, so the
 // order of the round-toward-zero accumulations - and with it every output bit - is fixed.
-template <int BN>
+template <int BN, bool SH = false>
 struct TcCfg {
   static constexpr int B_TILE = BN * TC_BK * 4;            // bytes of one of hi / lo
   static constexpr int ACC = BN / 2;                       // accumulator registers per thread: its row x BN/2 columns
-  static constexpr size_t SMEM = static_cast<size_t>(TC_A_STAGES) * TC_A_TILE +
-                                 static_cast<size_t>(TC_B_STAGES) * 2 * B_TILE + TC_TABLES + 1024;
-  static_assert(2 * BN <= 256, "accumulators must leave 256 TMEM columns for the A operand");
+  static constexpr int A_BYTES = SH ? TC_SH_STAGES * TC_SH_TILE : TC_A_STAGES * TC_A_TILE;   // 96 KB either way
+  // Pipeline depth.  The loop split(c) -> MMA(c) -> [TMEM stage free] -> split(c + T) and the weight prefetch
+  // MMA(c-1) done -> load B(c + B - 1) -> MMA(c + B - 1) make the chunk period max(issue, split, (issue + split) / (T-1)...,
+  // (issue + L2 latency) / (B - 1)).  At N = 128 the MMA issue (12 x 64 clk) hides both with T = 2 / B = 3 and TMEM / shared
+  // memory are full; at N <= 64 the issue is short (12 x ~35 clk per half) and the measured period was twice it
+  // (scripts/tc_layer_trace.py: 1715 clk vs 960 of issue), so those tiles take a third A stage (TMEM columns 128..511 are
+  // free next to <= 128 accumulator columns) and a fourth weight stage.
+  static constexpr int T_STAGES = BN <= 64 ? 3 : 2;
+  static constexpr int B_STAGES = BN <= 64 ? 4 : 3;
+  static constexpr uint32_t A_COL0 = 512u - T_STAGES * 128u;        // first TMEM column of the split A operand
+  static constexpr size_t SMEM = static_cast<size_t>(A_BYTES) + static_cast<size_t>(B_STAGES) * 2 * B_TILE + TC_TABLES +
+                                 (SH ? TC_SH_TABLES : 0) + 1024;
+  static_assert(2 * BN <= static_cast<int>(A_COL0), "accumulators must leave the A operand's TMEM columns free");
 };
 constexpr int kFlushChunks = 32;                // epoch length: K = 1024 per TMEM accumulation run
 constexpr int32_t kNoRow = -1;                  // tap-table entry of an inactive / padded source: an out-of-bounds TMA row reads zeros
@@ -215,20 +241,23 @@ __host__ __device__ __forceinline__ BalPlan bal_plan(long long tiles, long long 
   return p;
 }
 
-template <int BN>
+template <int BN, bool SH>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_conv_desc d, const float* __restrict__ wtc,
                                                                      const int splits, float* __restrict__ partial,
                                                                      const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, SH>;
   constexpr int TC_B_TILE = Cfg::B_TILE;
   constexpr int ACC = Cfg::ACC;
+  constexpr int TC_T_STAGES = Cfg::T_STAGES;
+  constexpr int TC_B_STAGES = Cfg::B_STAGES;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t bar_raw_full[TC_A_STAGES];   // raw A tile of the stage has landed (TMA transaction bytes)
   __shared__ __align__(8) uint64_t bar_raw_empty[TC_A_STAGES];  // ... has been read by the 8 split warps
-  __shared__ __align__(8) uint64_t bar_asplit[TC_T_STAGES];     // split A of the TMEM stage is stored (8 split warps)
-  __shared__ __align__(8) uint64_t bar_mma[TC_T_STAGES];        // chunk's MMAs done (2 issuers): TMEM A stage + B stage reusable
-  __shared__ __align__(8) uint64_t bar_b[TC_B_STAGES];     // weight image of the stage has landed (bulk copy)
+  __shared__ __align__(8) uint64_t bar_asplit[TC_T_STAGES_MAX]; // split A of the TMEM stage is stored (8 split warps)
+  __shared__ __align__(8) uint64_t bar_mma[TC_T_STAGES_MAX];    // chunk's MMAs done (2 issuers): TMEM A stage + B stage reusable
+  __shared__ __align__(8) uint64_t bar_b[TC_B_STAGES_MAX]; // weight image of the stage has landed (bulk copy)
+  __shared__ __align__(8) uint64_t bar_bfree[TC_B_STAGES_MAX];  // chunk's MMAs done (2 issuers): weight stage reusable
   __shared__ __align__(8) uint64_t bar_epoch;              // accumulation epoch complete (4 issuers)
   __shared__ uint32_t tmem_base_slot;
 
@@ -237,9 +266,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* sA_base = base;
-  unsigned char* sB_base = base + TC_A_STAGES * TC_A_TILE;
+  unsigned char* sB_base = base + Cfg::A_BYTES;
   int32_t* tab0 = reinterpret_cast<int32_t*>(sB_base + TC_B_STAGES * 2 * TC_B_TILE);   // [tap][row]: source row in x0, -1 = none
   int32_t* tab1 = tab0 + 9 * TC_BM;                                                    // ... in x1
+  // shared-tap gather tables (SH): extra source rows [src][dy][128], slots [src][dy][side][row], counters [src*3+dy], [6] = overflow
+  int32_t* xtra = tab1 + 9 * TC_BM;
+  uint16_t* slots = reinterpret_cast<uint16_t*>(xtra + 2 * 3 * TC_SH_EXTRA);
+  int* nx = reinterpret_cast<int*>(slots + 2 * 3 * 2 * TC_BM);
 
   if (tid == 0) {
     for (int s = 0; s < TC_A_STAGES; ++s) {
@@ -250,7 +283,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       mbar_init(smem_u32(&bar_asplit[s]), TC_SPLIT_WARPS);
       mbar_init(smem_u32(&bar_mma[s]), TC_ISSUERS);
     }
-    for (int s = 0; s < TC_B_STAGES; ++s) mbar_init(smem_u32(&bar_b[s]), 1);
+    for (int s = 0; s < TC_B_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_b[s]), 1);
+      mbar_init(smem_u32(&bar_bfree[s]), TC_ISSUERS);
+    }
     mbar_init(smem_u32(&bar_epoch), TC_ISSUERS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -287,6 +323,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   const uint32_t my_acc_addr = tmem_acc + lane_field + static_cast<uint32_t>(my_half * BN + my_ch * ACC);
   uint32_t mma_rounds = 0;                                       // chunks issued so far by this CTA (all tiles)
   uint32_t epochs = 0;                                           // epoch commits so far
+  uint32_t fill_rounds = 0;                                      // SH: raw-stage fills so far by this CTA (all tiles)
 
   // accumulators start (and are left by every drain) at zero: every MMA accumulates
 #pragma unroll
@@ -348,39 +385,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     const int n0 = nt * BN;
     TC_TILE_TRACE(0);
 
-    for (int e = tid; e < d.taps * TC_BM; e += TC_THREADS) {
-      const int tap = e / TC_BM, r = e - tap * TC_BM;
+    if (SH) {                                      // extras default to "no row" (the tail of a 4-row load group), counters to 0
+      for (int e = tid; e < 2 * 3 * TC_SH_EXTRA; e += TC_THREADS) xtra[e] = kNoRow;
+      if (tid < 8) nx[tid] = 0;
+    }
+    // thread t: tile row t % 256, taps [t / 256 * 5, ...): the output pixel is read and decoded once per row, the taps'
+    // gate / map lookups are independent loads
+    {
+      const int r = tid & (TC_BM - 1);
+      const int t_lo = (tid >> 8) * 5, t_hi = min(d.taps, t_lo + 5);
       const int m = m0 + r;
-      int32_t o0 = kNoRow, o1 = kNoRow;
-      if (m < rows) {
+      int n = 0, y = 0, x = 0;
+      const bool live = m < rows;
+      if (live && t_lo < t_hi) {
         const int p = d.pixels ? d.pixels[m] : m;
-        const int n = static_cast<int>(p / HW);
+        n = static_cast<int>(p / HW);
         const int rem = static_cast<int>(p - n * HW);
-        const int y = rem / d.W, x = rem - y * d.W;
-        int qy = y, qx = x;
-        if (d.taps == 9) { qy += tap / 3 - 1; qx += tap % 3 - 1; }
-        bool ok = pad_coord(qy, d.H, d.pad_mode);
-        ok = pad_coord(qx, d.W, d.pad_mode) && ok;
-        if (ok) {
-          const int q = (n * d.H + qy) * d.W + qx;
-          if (d.gate && !d.gate[q]) ok = false;
+        y = rem / d.W;
+        x = rem - y * d.W;
+      }
+      for (int tap = t_lo; tap < t_hi; ++tap) {
+        int32_t o0 = kNoRow, o1 = kNoRow;
+        if (live) {
+          int qy = y, qx = x;
+          if (d.taps == 9) { qy += tap / 3 - 1; qx += tap % 3 - 1; }
+          bool ok = pad_coord(qy, d.H, d.pad_mode);
+          ok = pad_coord(qx, d.W, d.pad_mode) && ok;
           if (ok) {
-            o1 = q;
-            int r0;
-            if (aligned_rows) {
-              r0 = m;
-            } else {
-              const int qs = (n * Hs + (qy >> d.shift0)) * Ws + (qx >> d.shift0);
-              r0 = d.map0 ? d.map0[qs] : qs;
+            const int q = (n * d.H + qy) * d.W + qx;
+            if (d.gate && !d.gate[q]) ok = false;
+            if (ok) {
+              o1 = q;
+              int r0;
+              if (aligned_rows) {
+                r0 = m;
+              } else {
+                const int qs = (n * Hs + (qy >> d.shift0)) * Ws + (qx >> d.shift0);
+                r0 = d.map0 ? d.map0[qs] : qs;
+              }
+              if (r0 >= 0) o0 = r0;
             }
-            if (r0 >= 0) o0 = r0;
           }
         }
+        tab0[tap * TC_BM + r] = o0;
+        tab1[tap * TC_BM + r] = o1;
       }
-      tab0[e] = o0;
-      tab1[e] = o1;
     }
     __syncthreads();
+    // SH: slot tables of the dx = -1 / +1 taps.  Tap (dy, dx) of tile row r reads source row s; if the centre tap of row
+    // r + dx reads the same s (the two output pixels are neighbours in the list) the row is already in slot r + dx of the
+    // (chunk, dy) stage, otherwise it becomes an extra (slot 256 + k).  Extras past the capacity switch the whole tile to
+    // one fill per chunk (group size 1).
+    int gsz = 1;
+    if (SH) {
+      const int nsrc = d.c1 > 0 ? 2 : 1;
+      for (int e = tid; e < nsrc * 3 * 2 * TC_BM; e += TC_THREADS) {
+        const int r = e % TC_BM;
+        int t = e / TC_BM;
+        const int side = t & 1; t >>= 1;
+        const int dy = t % 3, src = t / 3;
+        const int dx = side ? 1 : -1;
+        const int32_t* tb = src ? tab1 : tab0;
+        const int32_t sidx = tb[(dy * 3 + 1 + dx) * TC_BM + r];
+        uint16_t slot = kZeroSlot;
+        if (sidx >= 0) {
+          const int rn = r + dx;
+          if (rn >= 0 && rn < TC_BM && tb[(dy * 3 + 1) * TC_BM + rn] == sidx) {
+            slot = static_cast<uint16_t>(rn);
+          } else {
+            const int k = atomicAdd(&nx[src * 3 + dy], 1);
+            if (k < TC_SH_EXTRA) {
+              xtra[(src * 3 + dy) * TC_SH_EXTRA + k] = sidx;
+              slot = static_cast<uint16_t>(TC_BM + k);
+            } else {
+              nx[6] = 1;
+            }
+          }
+        }
+        slots[((src * 3 + dy) * 2 + side) * TC_BM + r] = slot;
+      }
+      __syncthreads();
+      gsz = nx[6] ? 1 : 3;
+    }
+    // raw-stage fills of this segment: fill index (tile-relative) of chunk c is c / gsz
+    const int f0 = cb / gsz;
+    const int nfills = (ce - 1) / gsz - f0 + 1;
+    const uint32_t fround0 = fill_rounds;
     TC_TILE_TRACE(1);
 
     const unsigned char* wtile = reinterpret_cast<const unsigned char*>(wtc) +
@@ -421,85 +511,152 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     // source rows (row indices from the tap table; -1 and channels past C are zero-filled by the TMA) into 512
     // contiguous, 128B-swizzled bytes of the raw stage and completes on the stage's mbarrier.  A chunk is 64 loads:
     // gather warp g issues groups g, g+6, ...  One load costs the issuing warp ~140 clk here - that is the TMA unit's
-    // queue, not the warp: the unit sustains one gather4 per ~25-30 clk per SM next to the weight copies, i.e. the
-    // L2->SM path at ~9 TB/s aggregate (A 32 KB + B <= 32 KB per chunk per SM).  Letting the split warps issue part
-    // of the loads (kSplitGather > 0) was measured and does not help.  Everything a load needs except the four row
-    // indices is made provably warp-uniform (shuffles), so ptxas keeps it in uniform registers across the unrolled
-    // loop; per load that leaves one LDS.128 + four R2URs.
-    constexpr int kMaxLoadsPerWarp = (TC_BM / 4 + TC_GATHER_WARPS - 1) / TC_GATHER_WARPS;
+    // queue, not the warp.  Everything a load needs except the four row indices is made provably warp-uniform
+    // (shuffles), so ptxas keeps it in uniform registers across the unrolled loop; per load that leaves one LDS.128 +
+    // four R2URs.
     const uint32_t sA_u = __shfl_sync(0xffffffffu, smem_u32(sA_base), 0);
-    auto issue_gathers = [&](int c, uint32_t round, int g0, int gstride, int gend, int nmax, bool expect) {
+    const int gw = warp - TC_SPLIT_WARPS;                               // gather warp index (valid for warps 8-13)
+    // ---- one-fill-per-chunk form (SH = false): chunk c -> raw stage round % 3, rows = the tap's table
+    constexpr int kMaxLoadsPerWarp = (TC_BM / 4 + TC_GATHER_WARPS - 1) / TC_GATHER_WARPS;
+    auto gather_chunk = [&](int c, uint32_t round) {
       const uint32_t st = round % TC_A_STAGES;
       const int rr = c / d.taps;                  // channel chunk outermost, taps innermost: the nine taps of a
       const int tap = c - rr * d.taps;            // chunk re-read (almost) the same rows while they are hot in L2
       const bool src1 = rr >= nch0;
       const int col = __shfl_sync(0xffffffffu, (src1 ? rr - nch0 : rr) * TC_BK, 0);
-      const uint32_t tab_u = __shfl_sync(0xffffffffu, smem_u32((src1 ? tab1 : tab0) + tap * TC_BM + 4 * g0), 0);
+      const uint32_t tab_u = __shfl_sync(0xffffffffu, smem_u32((src1 ? tab1 : tab0) + tap * TC_BM + 4 * gw), 0);
       const uint64_t tmp = reinterpret_cast<uint64_t>(src1 ? &tm1 : &tm0);
       const uint64_t tm_u = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp >> 32), 0)) << 32) |
                             __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp), 0);
       const uint32_t bar = __shfl_sync(0xffffffffu, smem_u32(&bar_raw_full[st]), 0);
-      const uint32_t dst_u = __shfl_sync(0xffffffffu, sA_u + st * TC_A_TILE + g0 * 512, 0);
-      if (expect && elect_one())
+      const uint32_t dst_u = __shfl_sync(0xffffffffu, sA_u + st * TC_A_TILE + gw * 512, 0);
+      if (gw == 0 && elect_one())
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(static_cast<uint32_t>(TC_A_TILE)) : "memory");
 #pragma unroll
       for (int i = 0; i < kMaxLoadsPerWarp; ++i) {
-        if (i < nmax && g0 + i * gstride < gend) {
+        if (gw + i * TC_GATHER_WARPS < TC_BM / 4) {
           int4 r4;
           asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n"
               : "=r"(r4.x), "=r"(r4.y), "=r"(r4.z), "=r"(r4.w)
-              : "r"(tab_u + static_cast<uint32_t>(i * gstride * 16)));
+              : "r"(tab_u + static_cast<uint32_t>(i * TC_GATHER_WARPS * 16)));
           if (elect_one())
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(
-                    dst_u + static_cast<uint32_t>(i * gstride * 512)),
+                    dst_u + static_cast<uint32_t>(i * TC_GATHER_WARPS * 512)),
                 "l"(tm_u), "r"(col), "r"(r4.x), "r"(r4.y), "r"(r4.z), "r"(r4.w), "r"(bar)
                 : "memory");
         }
       }
     };
-    constexpr int kSplitGather = 0;                                     // loads per split warp per chunk
-    constexpr int kGatherGroups = TC_BM / 4 - TC_SPLIT_WARPS * kSplitGather;   // groups left to the gather warps
-    static_assert(kGatherGroups <= kMaxLoadsPerWarp * TC_GATHER_WARPS, "issue_gathers unroll bound");
-    auto gather_chunk = [&](int c, uint32_t round) {                    // gather-warp share
-      issue_gathers(c, round, warp - TC_SPLIT_WARPS, TC_GATHER_WARPS, kGatherGroups, kMaxLoadsPerWarp, warp == TC_SPLIT_WARPS);
-    };
-    auto split_gather_chunk = [&](int c, uint32_t round) {              // split-warp share
-      issue_gathers(c, round, kGatherGroups + warp, TC_SPLIT_WARPS, TC_BM / 4, kSplitGather, false);
+    // ---- shared-tap form (SH = true): fill `fr` (tile-relative) = chunks fr*gsz .. of one (channel chunk, dy); slots
+    // 0..255 <- the centre tap's table, slots 256.. <- the (source, dy)'s extras; stage = global fill round % 2
+    constexpr int kMaxFillLoads = (TC_SH_ROWS / 4 + TC_GATHER_WARPS - 1) / TC_GATHER_WARPS;
+    auto issue_fill = [&](int fr, uint32_t fround) {
+      const uint32_t st = fround % TC_SH_STAGES;
+      const int c = fr * gsz;
+      const int rr = c / 9;
+      const int tap = c - rr * 9;                 // gsz == 3: the (dy, dx = -1) tap, centre = tap + 1; gsz == 1: the tap itself
+      const bool src1 = rr >= nch0;
+      const int sd = (src1 ? 3 : 0) + tap / 3;
+      const int col = __shfl_sync(0xffffffffu, (src1 ? rr - nch0 : rr) * TC_BK, 0);
+      const int ctap = gsz == 3 ? tap + 1 : tap;
+      const int ne = gsz == 3 ? min(nx[sd], TC_SH_EXTRA) : 0;
+      const int ngroups = __shfl_sync(0xffffffffu, TC_BM / 4 + ((ne + 3) >> 2), 0);
+      const uint32_t tab_u = __shfl_sync(0xffffffffu, smem_u32((src1 ? tab1 : tab0) + ctap * TC_BM), 0);
+      const uint32_t xtr_u = __shfl_sync(0xffffffffu, smem_u32(xtra + sd * TC_SH_EXTRA) - static_cast<uint32_t>(TC_BM * 4), 0);
+      const uint64_t tmp = reinterpret_cast<uint64_t>(src1 ? &tm1 : &tm0);
+      const uint64_t tm_u = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp >> 32), 0)) << 32) |
+                            __shfl_sync(0xffffffffu, static_cast<uint32_t>(tmp), 0);
+      const uint32_t bar = __shfl_sync(0xffffffffu, smem_u32(&bar_raw_full[st]), 0);
+      const uint32_t dst_u = __shfl_sync(0xffffffffu, sA_u + st * TC_SH_TILE, 0);
+      if (gw == 0 && elect_one())
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(static_cast<uint32_t>(ngroups * 512)) : "memory");
+#pragma unroll
+      for (int i = 0; i < kMaxFillLoads; ++i) {
+        const int g = gw + i * TC_GATHER_WARPS;   // warp-uniform
+        if (g < ngroups) {
+          int4 r4;
+          asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n"
+              : "=r"(r4.x), "=r"(r4.y), "=r"(r4.z), "=r"(r4.w)
+              : "r"((g < TC_BM / 4 ? tab_u : xtr_u) + static_cast<uint32_t>(g * 16)));
+          if (elect_one())
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(
+                    dst_u + static_cast<uint32_t>(g * 512)),
+                "l"(tm_u), "r"(col), "r"(r4.x), "r"(r4.y), "r"(r4.z), "r"(r4.w), "r"(bar)
+                : "memory");
+        }
+      }
     };
 
     if (warp < TC_SPLIT_WARPS) {
       // =================================================================================== split warps
       // raw fp32 row (128 B of the smem stage) -> hi / lo in tensor memory.  Thread = tile row `my_row` = TMEM lane.
-      if (kSplitGather > 0) {
-        split_gather_chunk(cb, round0);
-        if (len > 1) split_gather_chunk(cb + 1, round0 + 1);
-      }
+      // running position of chunk cb + c: tap, source, place in its fill group, fill round (no divisions in the loop)
+      int tapi = cb % 9, rri = cb / 9;
+      int gpos = cb % gsz;
+      uint32_t fround = fround0;
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
-        const uint32_t rs = round % TC_A_STAGES, ts = round & 1;
+        const uint32_t ts = round % TC_T_STAGES;
         epoch_boundary(c);
-        if (kSplitGather > 0 && c + 2 < len) {       // my share of the gather two chunks ahead (stage read by round-1: all 8 split warps done?)
-          const uint32_t r2 = round + 2, st2 = r2 % TC_A_STAGES;
-          if (c + 2 >= TC_A_STAGES) mbar_wait(smem_u32(&bar_raw_empty[st2]), ((r2 - TC_A_STAGES) / TC_A_STAGES) & 1, 0x38000u + round);
-          split_gather_chunk(cb + c + 2, r2);
-        }
         if (warp == 0) TC_TRACE(0, 0, c);
-        mbar_wait(smem_u32(&bar_raw_full[rs]), (round / TC_A_STAGES) & 1, 0x20000u + round);
+        const unsigned char* rowp;
+        uint32_t swz;                                   // row's swizzle key (slot & 7)
+        uint32_t release_bar = 0;                       // raw stage to hand back after this chunk (0 = keep)
+        bool zero_row = false;
+        if (SH) {
+          const uint32_t st = fround % TC_SH_STAGES;
+          if (c == 0 || gpos == 0) mbar_wait(smem_u32(&bar_raw_full[st]), (fround / TC_SH_STAGES) & 1, 0x20000u + round);
+          int slot = my_row;
+          if (gsz == 3 && gpos != 1) slot = slots[(((rri >= nch0 ? 3 : 0) + tapi / 3) * 2 + (gpos >> 1)) * TC_BM + my_row];
+          zero_row = slot == kZeroSlot;
+          if (zero_row) slot = my_row;
+          rowp = sA_base + st * TC_SH_TILE + slot * 128;
+          swz = static_cast<uint32_t>(slot & 7);
+          if (gpos == gsz - 1 || c == len - 1) release_bar = smem_u32(&bar_raw_empty[st]);
+          if (++gpos == gsz) { gpos = 0; ++fround; }
+          if (++tapi == 9) { tapi = 0; ++rri; }
+        } else {
+          const uint32_t rs = round % TC_A_STAGES;
+          mbar_wait(smem_u32(&bar_raw_full[rs]), (round / TC_A_STAGES) & 1, 0x20000u + round);
+          rowp = sA_base + rs * TC_A_TILE + my_row * 128;
+          swz = static_cast<uint32_t>(my_row & 7);
+          release_bar = smem_u32(&bar_raw_empty[rs]);
+        }
         if (warp == 0) TC_TRACE(0, 1, c);
         if (c == 0) TC_TILE_TRACE(2);
-        // TMEM A stage free?  It was read by the MMAs of round-2.
-        if (round >= 2) mbar_wait(smem_u32(&bar_mma[ts]), ((round - 2) >> 1) & 1, 0x28000u + round);
+        // N <= 64: the row's 128 bytes first (the raw stage is ready), then the wait for the TMEM A stage - the
+        // shared-memory latency overlaps the barrier's.  N = 128 keeps 64 accumulator registers per thread and has no
+        // room for the whole row: it reads 64 bytes at a time after the wait.
+        constexpr bool kEarly = BN <= 64;
+        uint4 rawv[kEarly ? 8 : 1];
+        if (kEarly) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            rawv[kEarly ? q : 0] = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(q) ^ swz) << 4));   // swizzle: conflict-free
+            if (SH && zero_row) rawv[kEarly ? q : 0] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          __syncwarp();
+          if (lane == 0 && release_bar) mbar_arrive(release_bar);       // raw stage may be overwritten
+        }
+        // TMEM A stage free?  It was read by the MMAs of round - T_STAGES.
+        if (round >= TC_T_STAGES) mbar_wait(smem_u32(&bar_mma[ts]), ((round - TC_T_STAGES) / TC_T_STAGES) & 1, 0x28000u + round);
         tc_fence_after();
         if (warp == 0) TC_TRACE(0, 2, c);
-        const unsigned char* rowp = sA_base + rs * TC_A_TILE + my_row * 128;
-        const uint32_t ta = tmem_acc + lane_field + 256u + ts * 128u + static_cast<uint32_t>(my_half * 64);
+        const uint32_t ta = tmem_acc + lane_field + Cfg::A_COL0 + ts * 128u + static_cast<uint32_t>(my_half * 64);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {              // 16 channels at a time
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4*>(rowp + (((4 * hf + q) ^ (my_row & 7)) << 4));   // swizzle: conflict-free
+            uint4 v;
+            if (kEarly) {
+              v = rawv[kEarly ? 4 * hf + q : 0];
+            } else {
+              v = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(4 * hf + q) ^ swz) << 4));
+              if (SH && zero_row) v = make_uint4(0u, 0u, 0u, 0u);
+            }
             const uint32_t raw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -510,8 +667,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           tmem_st16(ta + static_cast<uint32_t>(16 * hf), hi);
           tmem_st16(ta + 32u + static_cast<uint32_t>(16 * hf), lo);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar_raw_empty[rs]));      // raw stage may be overwritten
+        if (!kEarly) {
+          __syncwarp();
+          if (lane == 0 && release_bar) mbar_arrive(release_bar);       // raw stage may be overwritten
+        }
         if (warp == 0) TC_TRACE(0, 3, c);
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         tc_fence_before();
@@ -522,27 +681,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       }
     } else if (warp < TC_SPLIT_WARPS + TC_GATHER_WARPS) {
       // =================================================================================== gather warps
-      // Implicit im2col through the TMA: every `tile::gather4` load fetches the 128-byte channel slice of FOUR
-      // arbitrary source rows (row indices from the tap table; -1 and channels past C are zero-filled by the TMA)
-      // into 512 contiguous, 128B-swizzled bytes of the raw stage and completes on the stage's mbarrier.
-      // 64 loads per chunk, dealt round-robin to the gather warps; the LSU is not involved (a cp.async gather costs
-      // ~10 shared-memory wavefronts per instruction and made the kernel shared-memory bound).
       // the raw stages are free at the start of a tile (every split of the previous tile has completed)
-      gather_chunk(cb, round0);
-      if (len > 1) gather_chunk(cb + 1, round0 + 1);
+      if (SH) {
+        issue_fill(f0, fround0);
+        if (nfills > 1) issue_fill(f0 + 1, fround0 + 1);
+        int gpos = cb % gsz, j = 0;                      // chunk's place in its fill group, fill index within the segment
+        for (int c = 0; c < len; ++c) {
+          epoch_boundary(c);
+          if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 0, c);
+          // at the first chunk of fill j >= 1 the stage of fill j - 1 is about to be released: refill it with fill j + 1
+          if (gpos == 0 && j >= 1 && j + 1 < nfills) {
+            const uint32_t fr2 = fround0 + static_cast<uint32_t>(j + 1);
+            mbar_wait(smem_u32(&bar_raw_empty[fr2 % TC_SH_STAGES]), ((fr2 / TC_SH_STAGES) - 1) & 1, 0x30000u + fr2);
+            if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 1, c);
+            issue_fill(f0 + j + 1, fr2);
+          }
+          if (++gpos == gsz) { gpos = 0; ++j; }
+          if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 2, c);
+          if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 3, c);
+          if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
+        }
+      } else {
+        gather_chunk(cb, round0);
+        if (len > 1) gather_chunk(cb + 1, round0 + 1);
+        for (int c = 0; c < len; ++c) {
+          const uint32_t round = round0 + c;
+          epoch_boundary(c);
+          if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 0, c);
+          if (c + 2 < len) {
+            const uint32_t r2 = round + 2, st2 = r2 % TC_A_STAGES;
+            // stage st2 was last filled for round r2-3: wait until the split warps have read it
+            if (c + 2 >= TC_A_STAGES) mbar_wait(smem_u32(&bar_raw_empty[st2]), ((r2 - TC_A_STAGES) / TC_A_STAGES) & 1, 0x30000u + round);
+            if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 1, c);
+            gather_chunk(cb + c + 2, r2);
+          }
+          if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 2, c);
+          if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 3, c);
+          if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
+        }
+      }
+    } else if (warp == TC_WLOAD_WARP) {
+      // =================================================================================== weight loader
+      // One [hi | lo] image per chunk, B_STAGES - 1 chunks ahead of the MMAs, a single cp.async.bulk each.  The stage
+      // of chunk c + B - 1 is the one chunk c - 1 used: it is free when both issuers' MMAs of chunk c - 1 have
+      // completed (bar_bfree, committed by the issuers: its next completion after chunk c - 1 is chunk c - 1 + B, which
+      // needs the very load issued here - no phase can be skipped).  A warp of its own, so that this wait is not in
+      // the issuers' loop.
+      const uint32_t sB_u = __shfl_sync(0xffffffffu, smem_u32(sB_base), 0);
+      if (elect_one()) {
+        const unsigned char* w0 = wtile + static_cast<long long>(cb) * (2 * TC_B_TILE);
+        // the first B_STAGES - 1 weight images (their stages are free: every MMA of the previous tile has completed)
+        for (int k = 0; k < TC_B_STAGES - 1 && k < len; ++k)
+          bulk_g2s(sB_u + ((round0 + k) % TC_B_STAGES) * 2 * TC_B_TILE, w0 + static_cast<long long>(k) * (2 * TC_B_TILE), 2 * TC_B_TILE,
+                   smem_u32(&bar_b[(round0 + k) % TC_B_STAGES]));
+      }
+      __syncwarp();
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
         epoch_boundary(c);
-        if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 0, c);
-        if (c + 2 < len) {
-          const uint32_t r2 = round + 2, st2 = r2 % TC_A_STAGES;
-          // stage st2 was last filled for round r2-3: wait until the split warps have read it
-          if (c + 2 >= TC_A_STAGES) mbar_wait(smem_u32(&bar_raw_empty[st2]), ((r2 - TC_A_STAGES) / TC_A_STAGES) & 1, 0x30000u + round);
-          if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 1, c);
-          gather_chunk(cb + c + 2, r2);
+        if (c >= 1 && c + TC_B_STAGES - 1 < len) {
+          mbar_wait(smem_u32(&bar_bfree[(round - 1) % TC_B_STAGES]), ((round - 1) / TC_B_STAGES) & 1, 0x50000u + round);
+          if (elect_one()) {
+            const uint32_t ns = (round + TC_B_STAGES - 1) % TC_B_STAGES;
+            bulk_g2s(sB_u + ns * 2 * TC_B_TILE, wtile + static_cast<long long>(cb + c + TC_B_STAGES - 1) * (2 * TC_B_TILE),
+                     2 * TC_B_TILE, smem_u32(&bar_b[ns]));
+          }
+          __syncwarp();
         }
-        if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 2, c);
-        if (warp == TC_SPLIT_WARPS) TC_TRACE(1, 3, c);
         if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) epochs += 1;
       }
     } else {
@@ -551,31 +756,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       // operands derived from warp-uniform values) ptxas keeps the MMA operands in uniform registers and emits the
       // UTCHMMAs back to back: ~78 clk per instruction.  A `lane == 0` branch instead makes it wrap every MMA in an
       // ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~210 clk (scripts/bench_cu/mma_rate*.cu).
-      const int ih = warp - (TC_SPLIT_WARPS + TC_GATHER_WARPS);     // this issuer's M half = its accumulator
+      const int ih = warp - (TC_WLOAD_WARP + 1);                    // this issuer's M half = its accumulator
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_acc, 0);
       const uint32_t sB_u = __shfl_sync(0xffffffffu, smem_u32(sB_base), 0);
-      if (ih == 0 && elect_one()) {
-        const unsigned char* w0 = wtile + static_cast<long long>(cb) * (2 * TC_B_TILE);
-        bulk_g2s(sB_u + (round0 % TC_B_STAGES) * 2 * TC_B_TILE, w0, 2 * TC_B_TILE, smem_u32(&bar_b[round0 % TC_B_STAGES]));
-        if (len > 1)
-          bulk_g2s(sB_u + ((round0 + 1) % TC_B_STAGES) * 2 * TC_B_TILE, w0 + 2 * TC_B_TILE, 2 * TC_B_TILE,
-                   smem_u32(&bar_b[(round0 + 1) % TC_B_STAGES]));
-      }
-      __syncwarp();
       const uint32_t dh = tmem_u + static_cast<uint32_t>(ih * BN);
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
-        const uint32_t ts = round & 1;
+        const uint32_t ts = round % TC_T_STAGES;
         const uint32_t bs = round % TC_B_STAGES;
         epoch_boundary(c);
         if (ih == 0) TC_TRACE(2, 0, c);
-        mbar_wait(smem_u32(&bar_asplit[ts]), (round >> 1) & 1, 0x40000u + round);           // split A of this chunk is in TMEM
+        mbar_wait(smem_u32(&bar_b[bs]), (round / TC_B_STAGES) & 1, 0x48000u + round);        // weight image has landed (long ago)
         if (ih == 0) TC_TRACE(2, 1, c);
-        mbar_wait(smem_u32(&bar_b[bs]), (round / TC_B_STAGES) & 1, 0x48000u + round);        // weight image has landed
+        mbar_wait(smem_u32(&bar_asplit[ts]), (round / TC_T_STAGES) & 1, 0x40000u + round);   // split A of this chunk is in TMEM
         if (ih == 0) TC_TRACE(2, 2, c);
         tc_fence_after();
         const uint64_t b0 = umma_desc_sw128(sB_u + bs * 2 * TC_B_TILE);
-        const uint32_t ah = tmem_u + 256u + ts * 128u + static_cast<uint32_t>(ih * 64);
+        const uint32_t ah = tmem_u + Cfg::A_COL0 + ts * 128u + static_cast<uint32_t>(ih * 64);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < TC_BK / 8; ++ks) {
@@ -586,18 +783,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
             umma_tf32_ts(dh, a, bl, kIdesc, 1u);           // hi*lo
             umma_tf32_ts(dh, a, bh, kIdesc, 1u);           // hi*hi
           }
-          umma_commit(smem_u32(&bar_mma[ts]));
+          umma_commit(smem_u32(&bar_mma[ts]));             // TMEM A stage reusable
+          umma_commit(smem_u32(&bar_bfree[bs]));           // weight stage reusable
           if (((c + 1) % kFlushChunks == 0) || (c == len - 1)) umma_commit(smem_u32(&bar_epoch));
-          // weights two chunks ahead go into the stage chunk c-1 used: wait for that chunk's MMAs.  This costs
-          // nothing - chunk c's MMAs are queued behind them and chunk c+1's A cannot be split before they finish
-          // either (TMEM stage).  No phase aliasing: bar_mma[(round-1)&1] next completes for round+1, which needs
-          // this thread's own commit.
-          if (ih == 0 && c + 2 < len) {
-            if (c >= 1) mbar_wait(smem_u32(&bar_mma[(round - 1) & 1]), ((round - 1) >> 1) & 1, 0x50000u + round);
-            const uint32_t ns = (round + 2) % TC_B_STAGES;
-            bulk_g2s(sB_u + ns * 2 * TC_B_TILE, wtile + static_cast<long long>(cb + c + 2) * (2 * TC_B_TILE),
-                     2 * TC_B_TILE, smem_u32(&bar_b[ns]));
-          }
         }
         __syncwarp();
         if (ih == 0) TC_TRACE(2, 3, c);
@@ -605,6 +793,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       }
     }
     mma_rounds = round0 + static_cast<uint32_t>(len);
+    fill_rounds = fround0 + static_cast<uint32_t>(nfills);
     TC_TILE_TRACE(3);
 
     // ---- last epoch + epilogue (all 16 warps): bias, activation, one contiguous 256-byte store per thread
@@ -787,9 +976,11 @@ static int make_rows_map(CUtensorMap* tm, const float* x, int C, long long rows,
   return rc == CUDA_SUCCESS ? WMD_OK : WMD_ERR_UNSUPPORTED;
 }
 
-template <int BN>
+static int g_shared_taps = 1;      // 3x3 layers: one raw-stage fill per (chunk, dy) shared by the three dx taps (tuning / A-B knob)
+
+template <int BN, bool SH>
 static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStream_t stream) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, SH>;
   CUtensorMap tm0, tm1;
   {
     const long long px = static_cast<long long>(d.N) * d.H * d.W;
@@ -807,7 +998,7 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {   // outside the cache: set it on every launch
-    int rc = record(cudaFuncSetAttribute(conv_rows_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int rc = record(cudaFuncSetAttribute(conv_rows_tc_kernel<BN, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(Cfg::SMEM)));
     if (rc != WMD_OK) return rc;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
@@ -815,7 +1006,7 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN) * (splits > 0 ? splits : 1);
   const long long cap = sm_count();
   const int grid = splits == 0 ? static_cast<int>(cap) : static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
-  conv_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial, tm0, tm1);
+  conv_rows_tc_kernel<BN, SH><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial, tm0, tm1);
   int rc = launched();
   if (rc != WMD_OK || splits == 1) return rc;
   const int nchunks = d.taps * ((d.c0 + TC_BK - 1) / TC_BK + (d.c1 + TC_BK - 1) / TC_BK);
@@ -839,6 +1030,12 @@ extern "C" int wmd_debug_tc_tile_trace(long long* host_out) {
 #endif
 
 extern "C" int wmd_conv_tc_tile_n(int cout) { return wmd::tc_tile_n(cout); }
+
+extern "C" int wmd_conv_tc_set_shared_taps(int on) {
+  const int was = wmd::g_shared_taps;
+  if (on >= 0) wmd::g_shared_taps = on ? 1 : 0;
+  return was;
+}
 
 extern "C" size_t wmd_conv_tc_weight_floats(int cout, int c0, int c1, int taps) {
   using namespace wmd;
@@ -908,9 +1105,10 @@ extern "C" int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* dp, int splits, 
     if (splits == 0 && nchunks < 2) splits = 1;   // nothing to balance inside a one-chunk reduction
   }
   float* partial = static_cast<float*>(ws);
+  const bool sh = d.taps == 9 && g_shared_taps != 0;
   switch (tc_tile_n(d.cout)) {
-    case 128: return launch_tc<128>(d, splits, partial, as_stream(stream));
-    case 64: return launch_tc<64>(d, splits, partial, as_stream(stream));
-    default: return launch_tc<32>(d, splits, partial, as_stream(stream));
+    case 128: return sh ? launch_tc<128, true>(d, splits, partial, as_stream(stream)) : launch_tc<128, false>(d, splits, partial, as_stream(stream));
+    case 64: return sh ? launch_tc<64, true>(d, splits, partial, as_stream(stream)) : launch_tc<64, false>(d, splits, partial, as_stream(stream));
+    default: return sh ? launch_tc<32, true>(d, splits, partial, as_stream(stream)) : launch_tc<32, false>(d, splits, partial, as_stream(stream));
   }
 }

@@ -32,11 +32,31 @@ __device__ __forceinline__ float disp_of(float v, float scale, int clamp01) {
   return clamp01 ? fminf(fmaxf(v, 0.f), 1.f) : v;
 }
 
+// consumer epilogue of the reconstruction / its disparity plane (WMD_EPI_*, see wmd_head_idwt_desc)
+struct EpiArgs {
+  int mode;
+  float a, b, lo, hi;
+  float* out0;
+  float* out1;
+};
+__device__ __forceinline__ void epi_store(const EpiArgs& e, long long o, float recon, float dispv) {
+  if (e.mode == WMD_EPI_DISP_TO_DEPTH) {             // KITTI/layers.py:16-25
+    const float sd = __fadd_rn(e.a, __fmul_rn(e.b, dispv));
+    e.out0[o] = sd;
+    if (e.out1) e.out1[o] = __fdiv_rn(1.f, sd);
+  } else if (e.mode == WMD_EPI_DIV_CLAMP) {          // NYUv2/utils.py:219,229
+    float v = __fdiv_rn(recon, e.a);
+    if (e.b != 0.f) v = fminf(fmaxf(v, e.lo), e.hi);
+    e.out0[o] = v;
+  }
+}
+
 // VEC: W even; one thread = two coefficient columns = a 2x4 output patch (two float4 stores per plane).
 template <bool VEC>
 __global__ void __launch_bounds__(256) idwt_haar_kernel(const float* __restrict__ ll, const float* __restrict__ hf,
                                                         float* __restrict__ out, float* __restrict__ disp,
-                                                        float disp_scale, int clamp01, long long planes, int H, int W) {
+                                                        float disp_scale, int clamp01, long long planes, int H, int W,
+                                                        const EpiArgs epi) {
   const long long HW = static_cast<long long>(H) * W;
   const int Wv = VEC ? (W >> 1) : W;
   const long long total = planes * H * Wv;
@@ -69,6 +89,14 @@ __global__ void __launch_bounds__(256) idwt_haar_kernel(const float* __restrict_
             make_float4(disp_of(r1.x, disp_scale, clamp01), disp_of(r1.y, disp_scale, clamp01),
                         disp_of(r1.z, disp_scale, clamp01), disp_of(r1.w, disp_scale, clamp01));
       }
+      if (epi.mode) {
+        const float t4[4] = {r0.x, r0.y, r0.z, r0.w}, b4[4] = {r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          epi_store(epi, oofs + k, t4[k], disp_of(t4[k], disp_scale, clamp01));
+          epi_store(epi, oofs + 2 * W + k, b4[k], disp_of(b4[k], disp_scale, clamp01));
+        }
+      }
     } else {
       const Quad q = haar_synth(__ldg(pl), __ldg(ph), __ldg(ph + HW), __ldg(ph + 2 * HW));
       out[oofs] = q.y00; out[oofs + 1] = q.y01;
@@ -78,6 +106,12 @@ __global__ void __launch_bounds__(256) idwt_haar_kernel(const float* __restrict_
         disp[oofs + 1] = disp_of(q.y01, disp_scale, clamp01);
         disp[oofs + 2 * W] = disp_of(q.y10, disp_scale, clamp01);
         disp[oofs + 2 * W + 1] = disp_of(q.y11, disp_scale, clamp01);
+      }
+      if (epi.mode) {
+        epi_store(epi, oofs, q.y00, disp_of(q.y00, disp_scale, clamp01));
+        epi_store(epi, oofs + 1, q.y01, disp_of(q.y01, disp_scale, clamp01));
+        epi_store(epi, oofs + 2 * W, q.y10, disp_of(q.y10, disp_scale, clamp01));
+        epi_store(epi, oofs + 2 * W + 1, q.y11, disp_of(q.y11, disp_scale, clamp01));
       }
     }
   }
@@ -195,8 +229,8 @@ extern "C" int wmd_idwt_bilinear_f32(const float* ll, const float* hf, float* fu
   return launched();
 }
 
-extern "C" int wmd_idwt_haar_f32(const float* ll, const float* hf, float* out, float* disp, float disp_scale,
-                                 int clamp01, int N, int C, int H, int W, wmd_stream_t stream) {
+static int launch_idwt(const float* ll, const float* hf, float* out, float* disp, float disp_scale, int clamp01, int N,
+                       int C, int H, int W, const wmd::EpiArgs& epi, wmd_stream_t stream) {
   using namespace wmd;
   WMD_REQUIRE(ll && hf && out, WMD_ERR_ARG);
   WMD_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0, WMD_ERR_SHAPE);
@@ -206,10 +240,25 @@ extern "C" int wmd_idwt_haar_f32(const float* ll, const float* hf, float* out, f
   const long long work = planes * H * (vec ? W / 2 : W);
   const int grid = stride_grid(work, 256);
   if (vec)
-    idwt_haar_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(ll, hf, out, disp, disp_scale, clamp01, planes, H, W);
+    idwt_haar_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(ll, hf, out, disp, disp_scale, clamp01, planes, H, W, epi);
   else
-    idwt_haar_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(ll, hf, out, disp, disp_scale, clamp01, planes, H, W);
+    idwt_haar_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(ll, hf, out, disp, disp_scale, clamp01, planes, H, W, epi);
   return launched();
+}
+
+extern "C" int wmd_idwt_haar_f32(const float* ll, const float* hf, float* out, float* disp, float disp_scale,
+                                 int clamp01, int N, int C, int H, int W, wmd_stream_t stream) {
+  const wmd::EpiArgs none = {WMD_EPI_NONE, 0.f, 0.f, 0.f, 0.f, nullptr, nullptr};
+  return launch_idwt(ll, hf, out, disp, disp_scale, clamp01, N, C, H, W, none, stream);
+}
+
+extern "C" int wmd_idwt_haar_epi_f32(const float* ll, const float* hf, float* out, float* disp, float disp_scale,
+                                     int clamp01, int epi_mode, float epi_a, float epi_b, float epi_lo, float epi_hi,
+                                     float* epi_out0, float* epi_out1, int N, int C, int H, int W, wmd_stream_t stream) {
+  WMD_REQUIRE(epi_mode >= WMD_EPI_NONE && epi_mode <= WMD_EPI_DIV_CLAMP, WMD_ERR_ARG);
+  WMD_REQUIRE(epi_mode == WMD_EPI_NONE || epi_out0 != nullptr, WMD_ERR_ARG);
+  const wmd::EpiArgs epi = {epi_mode, epi_a, epi_b, epi_lo, epi_hi, epi_out0, epi_out1};
+  return launch_idwt(ll, hf, out, disp, disp_scale, clamp01, N, C, H, W, epi, stream);
 }
 
 extern "C" int wmd_dwt_haar_f32(const float* x, float* ll, float* hf, int N, int C, int H, int W,

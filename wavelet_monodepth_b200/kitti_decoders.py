@@ -173,6 +173,13 @@ class _WaveDecoderBase(nn.Module):
         self.factored_ll = os.environ.get("WMD_FACTORED_LL", "1") == "1"
         # compactions of the level's three active sets on parallel streams (WMD_OVERLAP_COMPACTION=0/1)
         self.overlap_compaction = os.environ.get("WMD_OVERLAP_COMPACTION", "1") == "1"
+        # tail of every level as one kernel: head gather-sum -> yh -> IDWT -> disp -> next level's threshold
+        # (wmd_head_idwt_f32; WMD_FUSED_TAIL=0/1).  Bit-identical to the head_gather + idwt_haar + range_thresh chain.
+        self.fused_tail = os.environ.get("WMD_FUSED_TAIL", "1") == "1"
+        # optional consumer epilogue of ("disp", 0), off by default: (min_depth, max_depth) adds ("scaled_disp", 0) and
+        # ("depth", 0) = disp_to_depth(("disp", 0), min_depth, max_depth) (KITTI/layers.py:16-25; evaluate_depth.py:193,
+        # test_simple.py:151), produced by the last level's fused tail
+        self.depth_range = None
 
     # ---- packed parameters ------------------------------------------------------------------
     def invalidate_packs(self):
@@ -291,6 +298,7 @@ class _WaveDecoderBase(nn.Module):
         h, w = feats[4].shape[2:]
         yl = yh = None
         counts = {}
+        next_thresh = None                 # per-sample threshold of the coming level, when the fused tail produced it
         for i in range(4, 0, -1):
             c = int(self.num_ch_dec[i])
             sparse = i in sparse_levels
@@ -303,7 +311,7 @@ class _WaveDecoderBase(nn.Module):
                 if i == 4:
                     masks = ops.level_masks(None, None, n=n, h=h, w=w, device=dev)
                 else:
-                    thresh = ops.range_thresh(yl, thresh_ratio)
+                    thresh = next_thresh if next_thresh is not None else ops.range_thresh(yl, thresh_ratio)
                     masks = ops.level_masks(yh, thresh)
             skip_gate = masks["S3"] if (sparse and self.gated_layout) else None
             skip_done = None
@@ -328,12 +336,13 @@ class _WaveDecoderBase(nn.Module):
                     # the three compactions are independent: S4 / S5 go to two side streams (own workspaces) and are
                     # joined where their lists are first read (upconv(i,1) / the head scatter)
                     (map4, pix4, off4), ev4 = ops.compact(masks["S4"], stream=_side_stream(dev, 1), ws_slot=1)
-                    (_, pix5, off5), ev5 = ops.compact(masks["S5"], want_idxmap=False, stream=_side_stream(dev, 2), ws_slot=2)
+                    (_, pix5, off5), ev5 = ops.compact(masks["S5"], want_idxmap=False, want_pixels=not self.fused_tail,
+                                                       stream=_side_stream(dev, 2), ws_slot=2)   # fused tail: the count only
                 gmap = ops.gate_map(masks["S1"], prev_map)
                 map2, pix2, off2 = ops.compact(masks["S2"])
                 if not self.overlap_compaction:
                     map4, pix4, off4 = ops.compact(masks["S4"])
-                    _, pix5, off5 = ops.compact(masks["S5"], want_idxmap=False)
+                    _, pix5, off5 = ops.compact(masks["S5"], want_idxmap=False, want_pixels=not self.fused_tail)
                 counts[i] = (off2, off4, off5)
                 xa = ops.conv_rows(x_rows, x_c, wp0, b0, c, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, map0=gmap,
                                    pixels=pix2, count=off2[n:], m_in0=_pm(lambda: (gmap >= 0).sum()))
@@ -380,8 +389,22 @@ class _WaveDecoderBase(nn.Module):
             if ll_in_gemm:
                 yl = ops.head_gather(z, 1, self.convs[("waveconv", i, 0)][2].conv.bias.detach(), n, 2 * h, 2 * w, 1,
                                      scale=float(2 ** i), act=ACT_SIGMOID, pad=PAD_REFLECT, col0=54)
-            yh = ops.head_gather(z, 6, bz, n, 2 * h, 2 * w, 3, scale=float(2 ** (i - 1)), act=ACT_SIGMOID, dual=True,
-                                 pad=PAD_REFLECT, **head_kw)
+            next_thresh = None
+            epi = ("disp_to_depth",) + tuple(self.depth_range) if (self.depth_range is not None and i == 1) else None
+            if self.fused_tail and (2 * w) % 4 == 0:
+                tail = ops.head_idwt(z, bz, yl, float(2 ** (i - 1)), 1.0 / 2 ** (i - 1), idxmap=head_kw.get("idxmap"),
+                                     mask=masks["S5"] if head_kw else None, pad=PAD_REFLECT, clamp01=True,
+                                     thresh_ratio=thresh_ratio if (with_masks and i > 1) else None, epilogue=epi)
+                yh, yl_next, disp = tail["yh"], tail["out"], tail["disp"]
+                next_thresh = tail.get("thresh")
+                if epi is not None:
+                    out[("scaled_disp", 0)], out[("depth", 0)] = tail["scaled_disp"], tail["depth"]
+            else:
+                if epi is not None:
+                    raise WmdError("depth_range needs the fused tail (fused_tail = True, even width)")
+                yh = ops.head_gather(z, 6, bz, n, 2 * h, 2 * w, 3, scale=float(2 ** (i - 1)), act=ACT_SIGMOID, dual=True,
+                                     pad=PAD_REFLECT, **head_kw)
+                yl_next, disp = ops.idwt_haar(yl, yh.unsqueeze(1), disp_scale=1.0 / 2 ** (i - 1), clamp01=True)
             out[("wavelets", i - 1, "LL")] = yl
             out[("wavelets", i - 1, "LH")] = yh[:, 0:1]
             out[("wavelets", i - 1, "HL")] = yh[:, 1:2]
@@ -389,7 +412,7 @@ class _WaveDecoderBase(nn.Module):
             if self.full_res_size is not None and i > 1:
                 out[("disp_full", i - 1)] = ops.idwt_bilinear(yl, yh.unsqueeze(1), self.full_res_size,
                                                                disp_scale=1.0 / 2 ** (i - 1), clamp01=True)
-            yl, disp = ops.idwt_haar(yl, yh.unsqueeze(1), disp_scale=1.0 / 2 ** (i - 1), clamp01=True)
+            yl = yl_next
             out[("disp", i - 1)] = disp
             x_rows, x_c = xb, c
             h, w = 2 * h, 2 * w

@@ -101,6 +101,9 @@ class _NyuWaveBase(nn.Module):
                                  padding=padding, is_depthwise=dw_upconv)
         self.wave3 = Conv3x3(features // 8, 3, padding=wave_pad, is_depthwise=dw_waveconv)
         self._depthwise = bool(dw_waveconv or dw_upconv)
+        # optional consumer epilogue of ("disp", 0), off by default: (div, lo, hi) adds ("depth", 0) =
+        # clamp(("disp", 0) / div, lo, hi) - NYUv2/utils.py:219,229 uses (100, 0.4, 10) - fused into the last IDWT
+        self.depth_epilogue = None
         self._packs = _PackCache()
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packs())
 
@@ -203,6 +206,9 @@ class _NyuWaveBase(nn.Module):
             if s == 0:
                 ll, disp = ops.idwt_haar(ll, hcoef.unsqueeze(1), disp_scale=0.5, clamp01=False)
                 out[("disp", 1)] = disp
+            elif self.depth_epilogue is not None:
+                ll, depth = ops.idwt_haar(ll, hcoef.unsqueeze(1), epilogue=("div_clamp",) + tuple(self.depth_epilogue))
+                out[("disp", 0)], out[("depth", 0)] = ll, depth
             else:
                 ll = ops.idwt_haar(ll, hcoef.unsqueeze(1))
                 out[("disp", 0)] = ll

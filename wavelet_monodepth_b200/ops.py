@@ -139,9 +139,27 @@ class _prof:
 
 
 # --------------------------------------------------------------------------- Haar
+def _epilogue_args(epilogue, like):
+    """(mode, a, b, lo, hi, out0, out1, names) of a consumer epilogue spec; see head_idwt."""
+    if epilogue is None:
+        return _lib.EPI_NONE, 0.0, 0.0, 0.0, 0.0, None, None, ()
+    if epilogue[0] == "disp_to_depth":
+        min_depth, max_depth = float(epilogue[1]), float(epilogue[2])
+        min_disp, max_disp = 1 / max_depth, 1 / min_depth                # Python doubles, as in the reference
+        return (_lib.EPI_DISP_TO_DEPTH, min_disp, max_disp - min_disp, 0.0, 0.0, torch.empty_like(like), torch.empty_like(like),
+                ("scaled_disp", "depth"))
+    if epilogue[0] == "div_clamp":
+        lo, hi = epilogue[2], epilogue[3]
+        return (_lib.EPI_DIV_CLAMP, float(epilogue[1]), 0.0 if lo is None else 1.0, 0.0 if lo is None else float(lo),
+                0.0 if lo is None else float(hi), torch.empty_like(like), None, ("depth",))
+    raise _lib.WmdError("unknown consumer epilogue %r" % (epilogue,))
+
+
 @_on_device
-def idwt_haar(ll, hf, disp_scale=None, clamp01=False):
-    """ll (N,C,H,W), hf (N,C,3,H,W) -> out (N,C,2H,2W) [, disp = clamp?(out*disp_scale)]."""
+def idwt_haar(ll, hf, disp_scale=None, clamp01=False, epilogue=None):
+    """ll (N,C,H,W), hf (N,C,3,H,W) -> out (N,C,2H,2W) [, disp = clamp?(out*disp_scale)] [, epilogue planes].
+
+    epilogue (consumer of the last level, see head_idwt): returns the extra plane(s) after out / disp."""
     lib = _lib.load()
     ll, hf = _dense(ll), _dense(hf)
     n, c, h, w = ll.shape
@@ -149,14 +167,22 @@ def idwt_haar(ll, hf, disp_scale=None, clamp01=False):
         raise _lib.WmdError("idwt_haar: hf shape %s does not match ll %s" % (tuple(hf.shape), tuple(ll.shape)))
     out = torch.empty((n, c, 2 * h, 2 * w), dtype=_f32, device=ll.device)
     disp = torch.empty_like(out) if disp_scale is not None else None
+    mode, ea, eb, elo, ehi, e0, e1, _ = _epilogue_args(epilogue, out)
+    extra = tuple(t for t in (e0, e1) if t is not None)
+    ret = (out,) + ((disp,) if disp_scale is not None else ()) + extra
     if out.numel() == 0:
-        return (out, disp) if disp_scale is not None else out
+        return ret if len(ret) > 1 else out
     with _prof('idwt_haar', lambda: dict(n=n, c=c, h=h, w=w, disp=disp is not None)):
-        rc = lib.wmd_idwt_haar_f32(_lib.ptr(ll), _lib.ptr(hf), _lib.ptr(out), _lib.ptr(disp),
-                                   float(disp_scale if disp_scale is not None else 1.0), int(bool(clamp01)),
-                                   n, c, h, w, _lib.stream_ptr())
+        if mode == _lib.EPI_NONE:
+            rc = lib.wmd_idwt_haar_f32(_lib.ptr(ll), _lib.ptr(hf), _lib.ptr(out), _lib.ptr(disp),
+                                       float(disp_scale if disp_scale is not None else 1.0), int(bool(clamp01)),
+                                       n, c, h, w, _lib.stream_ptr())
+        else:
+            rc = lib.wmd_idwt_haar_epi_f32(_lib.ptr(ll), _lib.ptr(hf), _lib.ptr(out), _lib.ptr(disp),
+                                           float(disp_scale if disp_scale is not None else 1.0), int(bool(clamp01)),
+                                           mode, ea, eb, elo, ehi, _lib.ptr(e0), _lib.ptr(e1), n, c, h, w, _lib.stream_ptr())
     _lib.check(rc, "wmd_idwt_haar_f32")
-    return (out, disp) if disp_scale is not None else out
+    return ret if len(ret) > 1 else out
 
 
 @_on_device
@@ -611,3 +637,47 @@ def head_gather(z, groups, bias, n, h, w, cout, scale=1.0, act=ACT_NONE, dual=Fa
                                      max_rows, _lib.ptr(out, _f32), cout, n, h, w, _lib.stream_ptr())
     _lib.check(rc, "wmd_head_gather_f32")
     return out
+
+
+@_on_device
+def head_idwt(z, bias, yl, scale, disp_scale, idxmap=None, mask=None, pad=PAD_REFLECT, clamp01=True, col0=0,
+              thresh_ratio=None, epilogue=None):
+    """Fused tail of a decoder level (wmd_head_idwt_f32): factored +/- head stage -> yh -> IDWT -> disp [-> consumer
+    epilogue] [-> next level's per-sample threshold].
+
+    z rows (>= col0 + 54 columns of tap products), yl (N,1,H,W).  Returns dict(yh (N,3,H,W), out (N,1,2H,2W), disp,
+    thresh (N,) if thresh_ratio is not None, plus the epilogue's planes).
+    epilogue: None | ("disp_to_depth", min_depth, max_depth) -> "scaled_disp", "depth" (KITTI/layers.py:16-25)
+                   | ("div_clamp", div, lo, hi)  (lo/hi None = no clamp) -> "depth" (NYUv2/utils.py:219,229)."""
+    lib = _lib.load()
+    yl = _dense(yl)
+    n, _, h, w = yl.shape
+    dev = yl.device
+    if col0 < 0 or col0 + 54 > z.shape[1] or col0 % 2:
+        raise _lib.WmdError("head_idwt: columns %d..%d do not fit rows of %d" % (col0, col0 + 54, z.shape[1]))
+    res = {"yh": torch.empty((n, 3, h, w), dtype=_f32, device=dev),
+           "out": torch.empty((n, 1, 2 * h, 2 * w), dtype=_f32, device=dev),
+           "disp": torch.empty((n, 1, 2 * h, 2 * w), dtype=_f32, device=dev)}
+    d = _lib.HeadIdwtDesc()
+    d.N, d.H, d.W = n, h, w
+    d.z, d.ldz = _lib.ptr(z, _f32) + 4 * col0, z.shape[1]
+    d.map, d.mask, d.bias = _lib.ptr(idxmap, _i32), _lib.ptr(mask, _u8), _lib.ptr(bias, _f32)
+    d.scale, d.pad_mode = float(scale), pad
+    d.ll, d.yh, d.out, d.disp = _lib.ptr(yl), _lib.ptr(res["yh"]), _lib.ptr(res["out"]), _lib.ptr(res["disp"])
+    d.disp_scale, d.clamp01 = float(disp_scale), int(bool(clamp01))
+    mode, ea, eb, elo, ehi, e0, e1, names = _epilogue_args(epilogue, res["out"])
+    d.epi_mode, d.epi_a, d.epi_b, d.epi_lo, d.epi_hi = mode, ea, eb, elo, ehi
+    d.epi_out0, d.epi_out1 = _lib.ptr(e0), _lib.ptr(e1)
+    for name, t in zip(names, (e0, e1)):
+        res[name] = t
+    ws = None
+    if thresh_ratio is not None:
+        res["thresh"] = torch.empty((n,), dtype=_f32, device=dev)
+        d.thresh, d.thresh_ratio = _lib.ptr(res["thresh"]), float(thresh_ratio)
+        ws = _scratch.range(dev, lib.wmd_head_idwt_ws_bytes(n, h, w))
+    if n == 0:
+        return res
+    with _prof('head_idwt', lambda: dict(n=n, h=h, w=w, mask=mask, epi=d.epi_mode, thresh=thresh_ratio is not None)):
+        rc = lib.wmd_head_idwt_f32(ctypes.byref(d), _lib.ptr(ws), ws.numel() if ws is not None else 0, _lib.stream_ptr())
+    _lib.check(rc, "wmd_head_idwt_f32")
+    return res
