@@ -180,6 +180,9 @@ typedef struct wmd_conv_desc {
   int32_t ldy;
   int32_t act;              /* WMD_ACT_* */
   float act_param;          /* LeakyReLU slope */
+  int32_t rows0;            /* rows allocated in x0, 0 = unknown.  Only used by the tensor-core engine's 1x1 form (taps == 1,
+                               map0 == NULL: output row m reads x0 row m): with rows0 > 0 it loads whole 256-row tiles by TMA
+                               (reads past rows0 are zero-filled) instead of gathering row by row */
 } wmd_conv_desc;
 
 int wmd_conv_rows_f32(const wmd_conv_desc* d, wmd_stream_t stream);

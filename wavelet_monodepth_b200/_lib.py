@@ -32,6 +32,7 @@ class ConvDesc(Structure):
         ("pixels", c_void_p), ("count", c_void_p), ("max_rows", c_int32),
         ("y", c_void_p), ("ldy", c_int32),
         ("act", c_int32), ("act_param", c_float),
+        ("rows0", c_int32),
     ]
 
 

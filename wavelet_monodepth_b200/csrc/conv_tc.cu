@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   const long long tiles = static_cast<long long>((rows + TC_BM - 1) / TC_BM) * n_tiles;
   const int Hs = d.H >> d.shift0, Ws = d.W >> d.shift0;
   const bool aligned_rows = (d.taps == 1 && d.map0 == nullptr);
+  const bool tiled_rows = aligned_rows && d.rows0 > 0;         // tm0 then has a 256-row box (launch_tc)
   // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                               (static_cast<uint32_t>(128 >> 4) << 24);
@@ -520,6 +521,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     constexpr int kMaxLoadsPerWarp = (TC_BM / 4 + TC_GATHER_WARPS - 1) / TC_GATHER_WARPS;
     auto gather_chunk = [&](int c, uint32_t round) {
       const uint32_t st = round % TC_A_STAGES;
+      if (tiled_rows) {
+        // 1x1 stages read tile rows m0 .. m0+255 of x0 as they are: ONE tiled TMA load (box = 256 rows x 32 channels, tm0 is
+        // encoded with that box by the host) instead of 64 four-row gathers - 690 vs 974 clk per chunk measured
+        // (scripts/bench_cu/tma_tile_rate.cu) and no issue pressure.  Rows past the tensor / channels past C read zeros.
+        if (gw == 0 && elect_one()) {
+          const uint32_t bar = smem_u32(&bar_raw_full[st]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(static_cast<uint32_t>(TC_A_TILE)) : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                  sA_u + st * TC_A_TILE),
+              "l"(reinterpret_cast<uint64_t>(&tm0)), "r"(c * TC_BK), "r"(m0), "r"(bar)
+              : "memory");
+        }
+        return;
+      }
       const int rr = c / d.taps;                  // channel chunk outermost, taps innermost: the nine taps of a
       const int tap = c - rr * d.taps;            // chunk re-read (almost) the same rows while they are hot in L2
       const bool src1 = rr >= nch0;
@@ -739,8 +755,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
         epoch_boundary(c);
-        if (c >= 1 && c + TC_B_STAGES - 1 < len) {
-          mbar_wait(smem_u32(&bar_bfree[(round - 1) % TC_B_STAGES]), ((round - 1) / TC_B_STAGES) & 1, 0x50000u + round);
+        if (c + TC_B_STAGES - 1 < len) {
+          // c == 0: the stage belonged to the previous tile's last chunk - free since the tile's closing barrier
+          if (c >= 1) mbar_wait(smem_u32(&bar_bfree[(round - 1) % TC_B_STAGES]), ((round - 1) / TC_B_STAGES) & 1, 0x50000u + round);
           if (elect_one()) {
             const uint32_t ns = (round + TC_B_STAGES - 1) % TC_B_STAGES;
             bulk_g2s(sB_u + ns * 2 * TC_B_TILE, wtile + static_cast<long long>(cb + c + TC_B_STAGES - 1) * (2 * TC_B_TILE),
@@ -959,7 +976,7 @@ static int tc_tile_n(int cout) { return cout >= 96 ? 128 : (cout >= 48 ? 64 : 32
 typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_rows_map(CUtensorMap* tm, const float* x, int C, long long rows, int ld) {
+static int make_rows_map(CUtensorMap* tm, const float* x, int C, long long rows, int ld, int box_rows = 1) {
   static TmEncodeFn encode = nullptr;
   if (!encode) {
     cudaDriverEntryPointQueryResult q;
@@ -969,7 +986,7 @@ static int make_rows_map(CUtensorMap* tm, const float* x, int C, long long rows,
   }
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(rows < 1 ? 1 : rows)};
   const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
-  const cuuint32_t box[2] = {TC_BK, 1}, estr[2] = {1, 1};
+  const cuuint32_t box[2] = {TC_BK, static_cast<cuuint32_t>(box_rows)}, estr[2] = {1, 1};
   const CUresult rc = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -985,7 +1002,9 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   {
     const long long px = static_cast<long long>(d.N) * d.H * d.W;
     const long long rows0 = static_cast<long long>(d.N) * (d.H >> d.shift0) * (d.W >> d.shift0);
-    int rc = make_rows_map(&tm0, d.x0, d.c0, rows0, d.ld0);
+    // 1x1 stage over its own rows (taps == 1, no index map): the kernel loads whole 256-row tiles
+    const bool tiled = (d.taps == 1 && d.map0 == nullptr && d.rows0 > 0);
+    int rc = make_rows_map(&tm0, d.x0, d.c0, tiled ? d.rows0 : rows0, d.ld0, tiled ? TC_BM : 1);
     if (rc != WMD_OK) return rc;
     if (d.c1 > 0) {
       rc = make_rows_map(&tm1, d.x1, d.c1, px, d.ld1);

@@ -45,7 +45,9 @@ __device__ __forceinline__ void epi_store(const EpiArgs& e, long long o, float r
     e.out0[o] = sd;
     if (e.out1) e.out1[o] = __fdiv_rn(1.f, sd);
   } else if (e.mode == WMD_EPI_DIV_CLAMP) {          // NYUv2/utils.py:219,229
-    float v = __fdiv_rn(recon, e.a);
+    // torch on CUDA evaluates `t / python_scalar` as t * (1 / scalar) (one IEEE division of the scalar, then a multiply):
+    // that is what the reference's `pred_y /= 100` computes where it runs (NYUv2/utils.py:219 after model.cuda())
+    float v = __fmul_rn(recon, __fdiv_rn(1.f, e.a));
     if (e.b != 0.f) v = fminf(fmaxf(v, e.lo), e.hi);
     e.out0[o] = v;
   }

@@ -48,7 +48,8 @@ __device__ __forceinline__ void epilogue(const wmd_head_idwt_desc& d, long long 
     d.epi_out0[o] = sd;
     if (d.epi_out1) d.epi_out1[o] = __fdiv_rn(1.f, sd);
   } else if (d.epi_mode == WMD_EPI_DIV_CLAMP) {       // NYUv2/utils.py:219,229 on the reconstruction
-    float v = __fdiv_rn(recon, d.epi_a);
+    // torch on CUDA evaluates `t / python_scalar` as t * (1 / scalar): what the reference's `pred_y /= 100` computes
+    float v = __fmul_rn(recon, __fdiv_rn(1.f, d.epi_a));
     if (d.epi_b != 0.f) v = fminf(fmaxf(v, d.epi_lo), d.epi_hi);
     d.epi_out0[o] = v;
   }
@@ -58,6 +59,9 @@ __global__ void __launch_bounds__(kFThreads) head_idwt_kernel(const wmd_head_idw
                                                               float* __restrict__ partial, int use_bulk) {
   __shared__ __align__(16) float s_ll[kFT_H][kFT_W];
   __shared__ __align__(16) uint8_t s_mask[kFT_H][kFT_W];
+  __shared__ __align__(16) float s_yh[3][kFT_H][kFT_W];        // the tile's coefficients (phase A -> phase B)
+  __shared__ uint16_t s_list[kFT_H * kFT_W];                   // the tile's active pixels
+  __shared__ int s_count;
   __shared__ __align__(8) uint64_t bar;
   __shared__ float s_mn[8], s_mx[8];
   __shared__ bool is_last;
@@ -105,16 +109,62 @@ __global__ void __launch_bounds__(kFThreads) head_idwt_kernel(const wmd_head_idw
   float b6[6];
 #pragma unroll
   for (int g = 0; g < 6; ++g) b6[g] = d.bias ? __ldg(d.bias + g) : 0.f;
+  for (int e = tid; e < 3 * kFT_H * kFT_W; e += kFThreads) (&s_yh[0][0][0])[e] = 0.f;    // coefficients default to zero
+  if (tid == 0) s_count = 0;
 
   if (use_bulk) {
+    __syncthreads();                                                     // s_count / s_yh initialised
     uint32_t done = 0;
-    while (!done)
+    for (uint32_t spin = 0; spin < (1u << 24) && !done; ++spin)          // bounded: a protocol bug traps instead of hanging
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                    : "=r"(done) : "r"(smem_addr(&bar)), "r"(0u) : "memory");
+    if (!done) __trap();
   } else {
     __syncthreads();
   }
 
+  // ---- phase A: the tile's ACTIVE pixels, dealt evenly to the threads (the gather-sum is the only irregular work: a
+  // thread that owned a fixed patch would serialise up to eight 9-tap gathers while its neighbours idle)
+  for (int e = tid; e < th * tw; e += kFThreads) {
+    const int r = e / tw, c = e - r * tw;
+    if (mask_n == nullptr || s_mask[r][c]) s_list[atomicAdd(&s_count, 1)] = static_cast<uint16_t>(r * kFT_W + c);
+  }
+  __syncthreads();
+  const int nact = s_count;
+  for (int i = tid; i < nact; i += kFThreads) {
+    const int e = s_list[i];
+    const int r = e / kFT_W, c = e - r * kFT_W;
+    const int y = y0 + r, x = x0 + c;
+    float s[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g) s[g] = b6[g];
+    int rows9[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {                                  // the nine index-map lookups first: independent loads
+      int qy = y + tap / 3 - 1, qx = x + tap % 3 - 1;
+      bool ok = pad_coord(qy, d.H, d.pad_mode);
+      ok = pad_coord(qx, d.W, d.pad_mode) && ok;
+      const int q = (n * d.H + qy) * d.W + qx;
+      rows9[tap] = ok ? (d.map ? __ldg(d.map + q) : q) : -1;
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {                                  // summed in tap order (the unfused chain's order)
+      if (rows9[tap] < 0) continue;
+      const float* zr = d.z + static_cast<long long>(rows9[tap]) * d.ldz + tap * 6;
+#pragma unroll
+      for (int g = 0; g < 6; g += 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(zr + g));
+        s[g] += v.x;
+        s[g + 1] += v.y;
+      }
+    }
+    s_yh[0][r][c] = d.scale * (activate(s[0], WMD_ACT_SIGMOID, 0.f) - activate(s[3], WMD_ACT_SIGMOID, 0.f));
+    s_yh[1][r][c] = d.scale * (activate(s[1], WMD_ACT_SIGMOID, 0.f) - activate(s[4], WMD_ACT_SIGMOID, 0.f));
+    s_yh[2][r][c] = d.scale * (activate(s[2], WMD_ACT_SIGMOID, 0.f) - activate(s[5], WMD_ACT_SIGMOID, 0.f));
+  }
+  __syncthreads();
+
+  // ---- phase B: the streaming part - yh rows out, synthesis, reconstruction / disparity rows out
   float mn = INFINITY, mx = -INFINITY;
   const int W2 = 2 * d.W;
   float* yh_n = d.yh + static_cast<long long>(n) * 3 * HW;
@@ -125,81 +175,39 @@ __global__ void __launch_bounds__(kFThreads) head_idwt_kernel(const wmd_head_idw
     const int r = 2 * warp + rr;
     const int y = y0 + r;
     if (r >= th || cx >= tw) continue;
-    float lh[4], hl[4], hh[4], llv[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      lh[k] = hl[k] = hh[k] = 0.f;
-      llv[k] = s_ll[r][min(cx + k, kFT_W - 1)];
-      const int x = x0 + cx + k;
-      if (x >= d.W) continue;
-      if (mask_n && !s_mask[r][cx + k]) continue;
-      float s[6];
-#pragma unroll
-      for (int g = 0; g < 6; ++g) s[g] = b6[g];
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        int qy = y + tap / 3 - 1, qx = x + tap % 3 - 1;
-        bool ok = pad_coord(qy, d.H, d.pad_mode);
-        ok = pad_coord(qx, d.W, d.pad_mode) && ok;
-        if (!ok) continue;
-        const int q = (n * d.H + qy) * d.W + qx;
-        const int row = d.map ? __ldg(d.map + q) : q;
-        if (row < 0) continue;
-        const float* zr = d.z + static_cast<long long>(row) * d.ldz + tap * 6;
-#pragma unroll
-        for (int g = 0; g < 6; g += 2) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(zr + g));
-          s[g] += v.x;
-          s[g + 1] += v.y;
-        }
-      }
-      lh[k] = d.scale * (activate(s[0], WMD_ACT_SIGMOID, 0.f) - activate(s[3], WMD_ACT_SIGMOID, 0.f));
-      hl[k] = d.scale * (activate(s[1], WMD_ACT_SIGMOID, 0.f) - activate(s[4], WMD_ACT_SIGMOID, 0.f));
-      hh[k] = d.scale * (activate(s[2], WMD_ACT_SIGMOID, 0.f) - activate(s[5], WMD_ACT_SIGMOID, 0.f));
-    }
-    const long long co = static_cast<long long>(y) * d.W + x0 + cx;
-    const bool full4 = cx + 3 < tw;
-    if (full4) {
-      *reinterpret_cast<float4*>(yh_n + co) = make_float4(lh[0], lh[1], lh[2], lh[3]);
-      *reinterpret_cast<float4*>(yh_n + HW + co) = make_float4(hl[0], hl[1], hl[2], hl[3]);
-      *reinterpret_cast<float4*>(yh_n + 2 * HW + co) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-    } else {
-      for (int k = 0; k < 4 && cx + k < tw; ++k) { yh_n[co + k] = lh[k]; yh_n[HW + co + k] = hl[k]; yh_n[2 * HW + co + k] = hh[k]; }
-    }
+    const float4 l4 = *reinterpret_cast<const float4*>(&s_ll[r][cx]);
+    const float4 a4 = *reinterpret_cast<const float4*>(&s_yh[0][r][cx]);
+    const float4 h4 = *reinterpret_cast<const float4*>(&s_yh[1][r][cx]);
+    const float4 d4 = *reinterpret_cast<const float4*>(&s_yh[2][r][cx]);
+    const float llv[4] = {l4.x, l4.y, l4.z, l4.w}, lh[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float hl[4] = {h4.x, h4.y, h4.z, h4.w}, hh[4] = {d4.x, d4.y, d4.z, d4.w};
+    const long long co = static_cast<long long>(y) * d.W + x0 + cx;      // W % 4 == 0: a lane's four columns are all inside
+    *reinterpret_cast<float4*>(yh_n + co) = a4;
+    *reinterpret_cast<float4*>(yh_n + HW + co) = h4;
+    *reinterpret_cast<float4*>(yh_n + 2 * HW + co) = d4;
     float top[8], bot[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) synth4(llv[k], lh[k], hl[k], hh[k], top[2 * k], top[2 * k + 1], bot[2 * k], bot[2 * k + 1]);
     const long long oo = out_n + static_cast<long long>(2 * y) * W2 + 2 * (x0 + cx);
-    const int nv = full4 ? 8 : 2 * (tw - cx);
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (k < nv) { mn = fnan_min(mn, fnan_min(top[k], bot[k])); mx = fnan_max(mx, fnan_max(top[k], bot[k])); }
-    if (full4) {
-      *reinterpret_cast<float4*>(d.out + oo) = make_float4(top[0], top[1], top[2], top[3]);
-      *reinterpret_cast<float4*>(d.out + oo + 4) = make_float4(top[4], top[5], top[6], top[7]);
-      *reinterpret_cast<float4*>(d.out + oo + W2) = make_float4(bot[0], bot[1], bot[2], bot[3]);
-      *reinterpret_cast<float4*>(d.out + oo + W2 + 4) = make_float4(bot[4], bot[5], bot[6], bot[7]);
-    } else {
-      for (int k = 0; k < nv; ++k) { d.out[oo + k] = top[k]; d.out[oo + W2 + k] = bot[k]; }
-    }
+    for (int k = 0; k < 8; ++k) { mn = fnan_min(mn, fnan_min(top[k], bot[k])); mx = fnan_max(mx, fnan_max(top[k], bot[k])); }
+    *reinterpret_cast<float4*>(d.out + oo) = make_float4(top[0], top[1], top[2], top[3]);
+    *reinterpret_cast<float4*>(d.out + oo + 4) = make_float4(top[4], top[5], top[6], top[7]);
+    *reinterpret_cast<float4*>(d.out + oo + W2) = make_float4(bot[0], bot[1], bot[2], bot[3]);
+    *reinterpret_cast<float4*>(d.out + oo + W2 + 4) = make_float4(bot[4], bot[5], bot[6], bot[7]);
     if (d.disp || d.epi_mode) {
       float dt[8], db[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) { dt[k] = disp_val(top[k], d.disp_scale, d.clamp01); db[k] = disp_val(bot[k], d.disp_scale, d.clamp01); }
       if (d.disp) {
-        if (full4) {
-          *reinterpret_cast<float4*>(d.disp + oo) = make_float4(dt[0], dt[1], dt[2], dt[3]);
-          *reinterpret_cast<float4*>(d.disp + oo + 4) = make_float4(dt[4], dt[5], dt[6], dt[7]);
-          *reinterpret_cast<float4*>(d.disp + oo + W2) = make_float4(db[0], db[1], db[2], db[3]);
-          *reinterpret_cast<float4*>(d.disp + oo + W2 + 4) = make_float4(db[4], db[5], db[6], db[7]);
-        } else {
-          for (int k = 0; k < nv; ++k) { d.disp[oo + k] = dt[k]; d.disp[oo + W2 + k] = db[k]; }
-        }
+        *reinterpret_cast<float4*>(d.disp + oo) = make_float4(dt[0], dt[1], dt[2], dt[3]);
+        *reinterpret_cast<float4*>(d.disp + oo + 4) = make_float4(dt[4], dt[5], dt[6], dt[7]);
+        *reinterpret_cast<float4*>(d.disp + oo + W2) = make_float4(db[0], db[1], db[2], db[3]);
+        *reinterpret_cast<float4*>(d.disp + oo + W2 + 4) = make_float4(db[4], db[5], db[6], db[7]);
       }
       if (d.epi_mode) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k < nv) { epilogue(d, oo + k, top[k], dt[k]); epilogue(d, oo + W2 + k, bot[k], db[k]); }
+        for (int k = 0; k < 8; ++k) { epilogue(d, oo + k, top[k], dt[k]); epilogue(d, oo + W2 + k, bot[k], db[k]); }
       }
     }
   }

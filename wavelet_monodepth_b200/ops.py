@@ -68,6 +68,15 @@ class _Scratch:
 _scratch = _Scratch()
 
 
+_SINGLE = []
+
+
+def _single_gpu():
+    if not _SINGLE:
+        _SINGLE.append(torch.cuda.device_count() <= 1)
+    return _SINGLE[0]
+
+
 def _on_device(fn):
     """Run a wrapper with its tensors' device current.
 
@@ -78,6 +87,8 @@ def _on_device(fn):
 
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
+        if _single_gpu():                      # one visible device: it is always the current one
+            return fn(*args, **kwargs)
         dev = None
         for a in args:
             if torch.is_tensor(a) and a.is_cuda:
@@ -513,6 +524,7 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
     d.pixels, d.count, d.max_rows = _lib.ptr(pixels, _i32), _lib.ptr(count, _i32), max_rows
     d.y, d.ldy = _lib.ptr(out, _f32), out.shape[1]
     d.act, d.act_param = act, float(act_param)
+    d.rows0 = int(x0.shape[0])
     info = lambda: dict(n=n, h=h, w=w, taps=taps, c0=c0, c1=c1, cout=cout, shift0=shift0, count=count,   # noqa: E731
                         max_rows=max_rows, m_in0=m_in0, m_in1=m_in1, kind=wpacked.kind)
     if wpacked.kind == "tc":
