@@ -206,8 +206,11 @@ int wmd_conv_rows_tc_f32(const wmd_conv_desc* d, wmd_stream_t stream);
  * splits = 0 selects BALANCED scheduling (data-parallel + stream-K): full rounds of tiles run whole; the (tile,
  * 32-channel chunk) units of the remainder tiles are dealt to the CTAs in equal contiguous ranges computed on the
  * device from the actual row count, so sparse layers whose tile count is data dependent still finish on all SMs
- * together; only remainder tiles cut by a range boundary (<= 8 segments) go through the workspace + fixed-order
- * reduce pass.  Its workspace size does not depend on the layer (SMs x 8 x 256 x 128 floats). */
+ * together; only remainder tiles cut by a range boundary (<= 8 segments) go through the workspace: the LAST segment of
+ * a tile to arrive (per-tile arrival counter) sums all of them in slab order - bias first - inside the same kernel, so
+ * there is no second pass and the bits do not depend on the arrival order.  Its workspace size does not depend on the
+ * layer (4 KiB of counters + SMs x 8 x 256 x 128 floats).  The first 4 KiB of `ws` (any splits) must be ZERO before the
+ * first launch that uses the buffer; every launch leaves them zero. */
 size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits);
 /* 3x3 layers gather the A operand once per (channel chunk, dy) and feed the three dx taps from that one shared-memory
  * stage through a per-tile slot table (sparse_conv3x3's nine shifted selections, KITTI/layers.py:445-453, read almost the

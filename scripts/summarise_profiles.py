@@ -74,3 +74,28 @@ if tc:
                     "step) and profiles/r01_conv_rows_ncu_full.csv (SIMT engine)" % (tag, len(tc)))
     json.dump(tj, open(traffic_path, "w"))
 print("launches:", len(step), "conv launches in capture:", len(data), "mean conv traffic:", tj.get("conv_rows_tc"))
+
+# ---- 3. second capture: the HBM-bound kernels (fused level tail = IDWT chain, layout moves)
+other = os.path.join(REPO, "gpurun_out", "prof_other.ncu-rep")
+if os.path.exists(other):
+    raw = subprocess.run(["ncu", "-i", other, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rd[0], rd[1], rd[2:]
+    idx = [hdr.index(w) for w in want if w in hdr]
+    with open(os.path.join(out_dir, "%s_idwt_layout_ncu_full.csv" % tag), "w") as f:
+        f.write("# %s: ncu --set full --clock-control none --import-source on -k regex:'head_idwt|nchw_to_rows' -s 9 -c 9 python "
+                "scripts/profile_step.py 2 (second decoder step, R50 1024x320 bs32): head_idwt = fused level tail (head gather-sum -> "
+                "yh -> IDWT -> disp -> next threshold), nchw_to_rows = layout moves of the encoder maps\n" % tag)
+        w = csv.writer(f)
+        w.writerow([hdr[i] for i in idx])
+        w.writerow([units[i] for i in idx])
+        for r in data:
+            w.writerow([r[i] for i in idx])
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    for key in ("head_idwt", "nchw_to_rows"):
+        v = [to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in data if key in r[it]]
+        if v:
+            tj[key] = int(sum(v) / len(v))
+    tj["source_other"] = "profiles/%s_idwt_layout_ncu_full.csv (mean dram read+write per launch)" % tag
+    json.dump(tj, open(traffic_path, "w"))
+    print("second capture:", len(data), "launches;", {k: tj.get(k) for k in ("head_idwt", "nchw_to_rows")})

@@ -199,14 +199,17 @@ __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  // the load and its wait are ONE asm statement: with two, the compiler may schedule uses of v[] between them (the wait
+  // has no register dependence on the load's outputs) and read registers the asynchronous load has not written yet -
+  // seen as a timing-dependent wrong accumulator slice on a cold first launch
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -223,6 +226,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // the last full round in keeps the ranges long (>= one tile's reduction), so a tile has <= 2 segments; only when
 // there is no full round at all (fewer tiles than CTAs) the ranges are shorter: U >= nchunks/6, <= 7 segments.
 constexpr int kBalSlabs = 8;                    // workspace slabs: CTAs x kBalSlabs tiles of 256 x N floats
+constexpr int kBalCounterBytes = 4096;          // balanced mode: per stream-K tile arrival counters at the head of the workspace
 struct BalPlan {
   long long rem_tile0;                          // first stream-K tile
   long long U;                                  // units (chunks) per CTA
@@ -260,6 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   __shared__ __align__(8) uint64_t bar_bfree[TC_B_STAGES_MAX];  // chunk's MMAs done (2 issuers): weight stage reusable
   __shared__ __align__(8) uint64_t bar_epoch;              // accumulation epoch complete (4 issuers)
   __shared__ uint32_t tmem_base_slot;
+  __shared__ int s_fixup;                                  // balanced mode: segments of the tile to reduce here (0 = not the last)
 
   // warp index through a shuffle: provably warp-uniform, so the role branches and everything the issuer warps
   // compute from it stay on the uniform datapath (see the issuer section)
@@ -653,12 +658,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
             rawv[kEarly ? q : 0] = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(q) ^ swz) << 4));   // swizzle: conflict-free
             if (SH && zero_row) rawv[kEarly ? q : 0] = make_uint4(0u, 0u, 0u, 0u);
           }
-          __syncwarp();
-          if (lane == 0 && release_bar) mbar_arrive(release_bar);       // raw stage may be overwritten
         }
         // TMEM A stage free?  It was read by the MMAs of round - T_STAGES.
         if (round >= TC_T_STAGES) mbar_wait(smem_u32(&bar_mma[ts]), ((round - TC_T_STAGES) / TC_T_STAGES) & 1, 0x28000u + round);
         tc_fence_after();
+        if (kEarly) {
+          // hand the raw stage back only once the row has provably arrived in registers: one dependent use of every
+          // loaded word precedes the arrive (a release does not wait for outstanding shared-memory loads by itself)
+          uint32_t touch = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) touch |= rawv[kEarly ? q : 0].x ^ rawv[kEarly ? q : 0].y ^ rawv[kEarly ? q : 0].z ^ rawv[kEarly ? q : 0].w;
+          asm volatile("" ::"r"(touch) : "memory");
+          __syncwarp();
+          if (lane == 0 && release_bar) mbar_arrive(release_bar);       // raw stage may be overwritten
+        }
         if (warp == 0) TC_TRACE(0, 2, c);
         const uint32_t ta = tmem_acc + lane_field + Cfg::A_COL0 + ts * 128u + static_cast<uint32_t>(my_half * 64);
 #pragma unroll
@@ -824,11 +837,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       if (m < rows && !whole) {
         // raw partial sums of this segment (bias / activation are applied by the reduce pass)
         if (balanced) {                                // compact workspace: [remainder tile][slab][256 rows][BN]
-          float* pr = partial + ((rem_t * plan.slabs + slab) * TC_BM + my_row) * BN + my_ch * ACC;
+          float* pr = partial + kBalCounterBytes / 4 + ((rem_t * plan.slabs + slab) * TC_BM + my_row) * BN + my_ch * ACC;
 #pragma unroll
-          for (int j = 0; j < ACC; j += 4) *reinterpret_cast<float4*>(pr + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          for (int j = 0; j < ACC; j += 4) __stcg(reinterpret_cast<float4*>(pr + j), make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
         } else {                                       // split-K: [slab][max_rows][ldy]
-          float* pr = partial + (static_cast<long long>(slab) * d.max_rows + m) * d.ldy;
+          float* pr = partial + kBalCounterBytes / 4 + (static_cast<long long>(slab) * d.max_rows + m) * d.ldy;
 #pragma unroll
           for (int j = 0; j < ACC; j += 4) {
             const int co = n0 + my_ch * ACC + j;     // ldy % 4 == 0: a quad that starts below cout stays inside the row
@@ -854,6 +867,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
               if (co + 1 < d.cout) yr[co + 1] = o.y;
               if (co + 2 < d.cout) yr[co + 2] = o.z;
               if (co + 3 < d.cout) yr[co + 3] = o.w;
+            }
+          }
+        }
+      }
+    }
+    // ---- balanced mode, stream-K fix-up: the LAST segment of a cut tile to arrive (arrival counter per tile, left at zero
+    // for the next launch) sums all segments in slab order - bias first, the order of every earlier version - applies the
+    // activation and writes the rows.  No CTA waits for another one and the result does not depend on who is last.
+    if (balanced && !whole) {
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const long long first = (rem_t * nchunks) / U, last = ((rem_t + 1) * nchunks - 1) / U;
+        const int nseg = static_cast<int>(last - first + 1);
+        unsigned* cnt = reinterpret_cast<unsigned*>(partial) + rem_t;
+        const unsigned t = atomicAdd(cnt, 1u);
+        s_fixup = (t == static_cast<unsigned>(nseg - 1)) ? nseg : 0;
+        if (s_fixup) *cnt = 0u;
+      }
+      __syncthreads();
+      const int nseg = s_fixup;
+      const int m = m0 + my_row;
+      if (nseg > 0 && m < rows) {
+        __threadfence();
+        const float* pb = partial + kBalCounterBytes / 4 + (rem_t * plan.slabs * TC_BM + my_row) * BN + my_ch * ACC;
+        float* yr = d.y + static_cast<long long>(m) * d.ldy;
+#pragma unroll
+        for (int j = 0; j < ACC; j += 4) {
+          const int co = n0 + my_ch * ACC + j;
+          if (co < d.cout) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d.bias) {
+              v.x = __ldg(d.bias + co);
+              if (co + 1 < d.cout) v.y = __ldg(d.bias + co + 1);
+              if (co + 2 < d.cout) v.z = __ldg(d.bias + co + 2);
+              if (co + 3 < d.cout) v.w = __ldg(d.bias + co + 3);
+            }
+            for (int sidx = 0; sidx < nseg; ++sidx) {
+              const float4 p = __ldcg(reinterpret_cast<const float4*>(pb + static_cast<long long>(sidx) * TC_BM * BN + j));
+              v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+            }
+            v.x = activate(v.x, d.act, d.act_param); v.y = activate(v.y, d.act, d.act_param);
+            v.z = activate(v.z, d.act, d.act_param); v.w = activate(v.w, d.act, d.act_param);
+            if (co + 3 < d.cout) {                   // balanced mode requires ldy % 4 == 0 and a 16-byte aligned y
+              *reinterpret_cast<float4*>(yr + co) = v;
+            } else {
+              yr[co] = v.x;
+              if (co + 1 < d.cout) yr[co + 1] = v.y;
+              if (co + 2 < d.cout) yr[co + 2] = v.z;
             }
           }
         }
@@ -918,6 +980,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
 __global__ void tc_reduce_kernel(const float* __restrict__ partial, int splits, int grid, int BN, int nchunks,
                                  const float* __restrict__ bias, float* __restrict__ y, int ldy, int cout,
                                  const int32_t* __restrict__ count, int max_rows, int act, float act_param) {
+  partial += kBalCounterBytes / 4;                   // the workspace starts with the balanced mode's arrival counters (kept zero)
   const int rows = count ? min(*count, max_rows) : max_rows;
   const long long slab_sz = static_cast<long long>(max_rows) * ldy;
   const int n_tiles = (cout + BN - 1) / BN;
@@ -1027,11 +1090,10 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   const int grid = splits == 0 ? static_cast<int>(cap) : static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
   conv_rows_tc_kernel<BN, SH><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial, tm0, tm1);
   int rc = launched();
-  if (rc != WMD_OK || splits == 1) return rc;
+  if (rc != WMD_OK || splits <= 1) return rc;      // whole tiles, or balanced: the kernel's own fix-up finishes cut tiles
   const int nchunks = d.taps * ((d.c0 + TC_BK - 1) / TC_BK + (d.c1 + TC_BK - 1) / TC_BK);
   const long long all_tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN);
-  // balanced: only the stream-K tiles (fewer than two rounds) can have partial sums
-  const long long red_grid = splits == 0 ? (all_tiles < 2 * cap ? all_tiles : 2 * cap) : (all_tiles < 8 * cap ? all_tiles : 8 * cap);
+  const long long red_grid = all_tiles < 8 * cap ? all_tiles : 8 * cap;
   tc_reduce_kernel<<<static_cast<int>(red_grid < 1 ? 1 : red_grid), 256, 0, stream>>>(partial, splits, grid, BN, nchunks, d.bias, d.y, d.ldy, d.cout,
                                                               d.count, d.max_rows, d.act, d.act_param);
   return launched();
@@ -1077,8 +1139,8 @@ extern "C" int wmd_pack_conv_weight_tc_f32(const float* w, float* packed, int Co
 extern "C" size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits) {
   if (splits == 1) return 0;
   if (splits == 0)   // balanced: [stream-K tile][slab][256 rows][N <= 128] floats, tiles x slabs <= CTAs x kBalSlabs whatever the layer size
-    return static_cast<size_t>(wmd::sm_count()) * wmd::kBalSlabs * wmd::TC_BM * 128 * sizeof(float);
-  return static_cast<size_t>(splits) * static_cast<size_t>(max_rows) * static_cast<size_t>(ldy) * sizeof(float);
+    return wmd::kBalCounterBytes + static_cast<size_t>(wmd::sm_count()) * wmd::kBalSlabs * wmd::TC_BM * 128 * sizeof(float);
+  return wmd::kBalCounterBytes + static_cast<size_t>(splits) * static_cast<size_t>(max_rows) * static_cast<size_t>(ldy) * sizeof(float);
 }
 
 extern "C" int wmd_conv_rows_tc_f32(const wmd_conv_desc* dp, wmd_stream_t stream) {

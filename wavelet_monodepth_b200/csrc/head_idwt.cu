@@ -147,15 +147,22 @@ __global__ void __launch_bounds__(kFThreads) head_idwt_kernel(const wmd_head_idw
       const int q = (n * d.H + qy) * d.W + qx;
       rows9[tap] = ok ? (d.map ? __ldg(d.map + q) : q) : -1;
     }
+    // all 27 loads first (a missing tap reads row 0 and is zeroed: + 0.0f leaves the sum's bits), then the sums in tap
+    // order - the order of the unfused chain
+    float2 v[9][3];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {                                  // summed in tap order (the unfused chain's order)
+    for (int tap = 0; tap < 9; ++tap) {
+      const float* zr = d.z + static_cast<long long>(max(rows9[tap], 0)) * d.ldz + tap * 6;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) v[tap][g] = __ldg(reinterpret_cast<const float2*>(zr + 2 * g));
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
       if (rows9[tap] < 0) continue;
-      const float* zr = d.z + static_cast<long long>(rows9[tap]) * d.ldz + tap * 6;
 #pragma unroll
-      for (int g = 0; g < 6; g += 2) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(zr + g));
-        s[g] += v.x;
-        s[g + 1] += v.y;
+      for (int g = 0; g < 3; ++g) {
+        s[2 * g] += v[tap][g].x;
+        s[2 * g + 1] += v[tap][g].y;
       }
     }
     s_yh[0][r][c] = d.scale * (activate(s[0], WMD_ACT_SIGMOID, 0.f) - activate(s[3], WMD_ACT_SIGMOID, 0.f));

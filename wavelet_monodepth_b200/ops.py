@@ -57,7 +57,14 @@ class _Scratch:
         return self._get(self._key("range", device), device, nbytes, 1 << 16, True)    # zeroed once; kernel keeps it zero
 
     def splitk(self, device, nbytes):
-        return self._get(self._key("splitk", device), device, (nbytes + 15) // 16 * 16, 16, False).view(_f32)
+        """Split-K / stream-K workspace.  Its first 4 KiB hold the balanced mode's per-tile arrival counters, which must be
+        zero before the first launch (the kernel leaves them zeroed): cleared once, when the buffer is created."""
+        key = self._key("splitk", device)
+        had = self.bufs.get(key)
+        buf = self._get(key, device, (nbytes + 15) // 16 * 16, 4096, False)
+        if buf is not had:
+            buf[:4096].zero_()
+        return buf.view(_f32)
 
     def compact(self, device, nbytes, slot=0):
         """slot: compactions that may run concurrently need different workspaces (side streams have their own key
