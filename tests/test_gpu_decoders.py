@@ -567,3 +567,18 @@ def test_nyu_consumer_epilogue_depth_div_clamp():
     assert torch.equal(depth, torch.clamp(out / 100, min=0.4, max=10))
     _, depth2 = ops.idwt_haar(yl, yh, epilogue=("div_clamp", 100.0, None, None))
     assert torch.equal(depth2, out / 100)
+
+
+def test_cold_first_launch_equals_warm_launches_in_a_fresh_process():
+    """Regression for two timing-dependent races that only showed on the COLD first launch of a kernel instantiation
+    (registers of an asynchronous tcgen05.ld read before its wait; a raw stage handed back to the TMA before the row's
+    shared-memory loads had landed): a fresh process runs the sparse decoder three times and every libwmd op's outputs
+    of forward 0 must equal those of forwards 1 and 2 bit for bit (scripts/probe_determinism.py)."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(repo, "scripts", "probe_determinism.py"), "r18"], capture_output=True,
+                         text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "done" in res.stdout and "DIFF" not in res.stdout and "shape" not in res.stdout, res.stdout[-3000:]
