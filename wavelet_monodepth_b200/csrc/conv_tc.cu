@@ -404,11 +404,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       int n = 0, y = 0, x = 0;
       const bool live = m < rows;
       if (live && t_lo < t_hi) {
-        const int p = d.pixels ? d.pixels[m] : m;
-        n = static_cast<int>(p / HW);
-        const int rem = static_cast<int>(p - n * HW);
-        y = rem / d.W;
-        x = rem - y * d.W;
+        const unsigned p = static_cast<unsigned>(d.pixels ? d.pixels[m] : m);     // < 2^31 (checked by the host): 32-bit divisions
+        const unsigned hw = static_cast<unsigned>(HW);
+        n = static_cast<int>(p / hw);
+        const unsigned rem = p - static_cast<unsigned>(n) * hw;
+        y = static_cast<int>(rem / static_cast<unsigned>(d.W));
+        x = static_cast<int>(rem - static_cast<unsigned>(y) * static_cast<unsigned>(d.W));
       }
       for (int tap = t_lo; tap < t_hi; ++tap) {
         int32_t o0 = kNoRow, o1 = kNoRow;

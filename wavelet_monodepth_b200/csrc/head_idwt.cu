@@ -6,7 +6,7 @@
 // min / max while it is produced.  Algorithmic bytes per coefficient pixel: 4 (ll) + 1 (mask) in, 12 (yh) + 16 (out) +
 // 16 (disp) out, + 9 x 24 B of tap products per ACTIVE pixel (L2-resident rows written by the kernel before).
 //
-// Tile = 16 coefficient rows x 128 columns per CTA (256 threads: warp w owns rows 2w, 2w+1; lane owns 4 columns).  The
+// Tile = 8 coefficient rows x 128 columns per CTA (128 threads: warp w owns rows 2w, 2w+1; lane owns 4 columns).  The
 // ll rows and the mask rows of the tile are staged into shared memory by the TMA (one cp.async.bulk per row segment,
 // completion by mbarrier transaction bytes) while the threads fetch the index-map rows; every global store is a full
 // 128-bit, 512-byte-per-warp row segment.  Arithmetic: the coefficient is  scale * (sigmoid(s+) - sigmoid(s-))  with
@@ -18,7 +18,7 @@ namespace wmd {
 
 #define WMD_S 0.70710678118654752440f
 
-constexpr int kFT_H = 16, kFT_W = 128, kFThreads = 256;
+constexpr int kFT_H = 8, kFT_W = 128, kFThreads = 128;    // small CTAs: many in flight per SM hide the gather / staging latency
 
 __device__ __forceinline__ float fnan_min(float a, float b) { return (a != a || b != b) ? NAN : fminf(a, b); }
 __device__ __forceinline__ float fnan_max(float a, float b) { return (a != a || b != b) ? NAN : fmaxf(a, b); }

@@ -447,7 +447,7 @@ def tc_splits(max_rows, cout, nchunks, device, ldy=None):
     return 0 if nchunks >= TC_BALANCE_MIN_CHUNKS else 1
 
 
-TC_BALANCE_MIN_CHUNKS = 80
+TC_BALANCE_MIN_CHUNKS = int(__import__("os").environ.get("WMD_TC_BALANCE_MIN_CHUNKS", "80"))
 
 
 class PackedW:
