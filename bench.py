@@ -183,6 +183,9 @@ def account(name, info):
         return px + (4 * px if info["idxmap"] else 0) + (4 * m if info["pixels"] else 0), 0
     if name == "gate_map":
         return 9 * info["count"], 0
+    if name == "gather_rows_list":
+        m = min(_as_int(info["count"], info["max_rows"]), info["max_rows"])
+        return 8 * info["c"] * m + 4 * m, 0
     if name in ("nchw_to_rows", "rows_to_nchw"):
         px = _as_int(info.get("marked"), info["n"] * info["hw"])      # gated move: only the marked pixels' rows
         return 8 * info["c"] * px + (info["n"] * info["hw"] if info.get("marked") is not None else 0), 0
@@ -699,10 +702,8 @@ def run_native(args, rank, world, local_rank):
         o = lst["out"]
         h2d = sum(host[k].numel() * 4 for k in dma)
         in_place = 0
-        for k in zero_copy:                                          # 128-byte requests the gated move issued to the host
-            up = o[("upsample_mask", k)].reshape(n_local, -1)
-            groups = int(up.reshape(n_local, -1, 32).any(-1).sum().item()) if up.shape[1] % 32 == 0 else up.numel() // 32
-            in_place += groups * 128 * host[k].shape[1]
+        for k in zero_copy:                                          # rows the list-based gather read from host memory
+            in_place += int(o[("upsample_mask", k)].sum().item()) * host[k].shape[1] * 4
         del graphs_e2e, bufs, st
         torch.cuda.empty_cache()
         return ms_, h2d, in_place
@@ -717,7 +718,7 @@ def run_native(args, rank, world, local_rank):
         # further variants: the listed skip map(s) stay in pinned host memory and the gated layout move reads only the
         # 32-pixel groups under the level's upsample mask, in place, across PCIe (graphs captured with gated_layout on)
         was = dec.gated_layout
-        dec.gated_layout = True
+        dec.gated_layout = not dec.compact_skip      # compact_skip (default) reads host maps through the list-based gather
         best = None
         try:
             for spec in args.e2e_zero_copy.split(";"):
@@ -740,9 +741,9 @@ def run_native(args, rank, world, local_rank):
             zc_ms, zc_h2d, zc_in_place, zc = best
             e2e_ms, e2e_h2d = zc_ms, zc_h2d + zc_in_place
             e2e_note = ("pinned host features; the other maps DMA-copied one step ahead on a copy stream, skip map(s) %s read in "
-                        "place from pinned host memory by the gated layout move (only 32-pixel groups under the level's "
-                        "upsample mask cross PCIe: %.0f MB of %.0f MB); h2d_bytes_per_step = DMA bytes + those in-place "
-                        "reads; PCIe-bound" % (list(zc), zc_in_place / 1e6, sum(host[k].numel() * 4 for k in zc) / 1e6))
+                        "place from pinned host memory by the list-based gather of the level's upsample-mask pixels (only "
+                        "those rows cross PCIe: %.0f MB of %.0f MB, plus sector overfetch); h2d_bytes_per_step = DMA bytes + "
+                        "those in-place reads; PCIe-bound" % (list(zc), zc_in_place / 1e6, sum(host[k].numel() * 4 for k in zc) / 1e6))
     e2e_value = n_global * args.steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if sampler else None
 
@@ -864,8 +865,9 @@ def run_native(args, rank, world, local_rank):
                                 "overlapped with the next step, the last one inside the region)",
                 "launch_mode": "CUDA graph replay (graphs.GraphedSparseDecoder)" if use_graph else "eager",
                 "head_1x1_stages": "fused (head_mlp) on levels 2, 1" if dec.fused_heads else "two gather-GEMM launches per level",
-                "layout_moves": "%s, %s" % ("gated by the upsample mask" if dec.gated_layout else "whole maps",
-                                            "side stream" if dec.overlap_layout else "in order"),
+                "layout_moves": ("sparse levels: list-based gather of the upsample-mask pixels only (compact skip rows); dense level: whole maps"
+                                 if dec.compact_skip else "%s, %s" % ("gated by the upsample mask" if dec.gated_layout else "whole maps",
+                                                                      "side stream" if dec.overlap_layout else "in order")),
             },
             "value_eager": {"value": round(value_eager, 1), "unit": UNIT, "ms_per_step": round(ms_eager / args.steps, 3),
                             "note": "same step issued launch by launch from Python (no CUDA graph)"},
@@ -906,7 +908,7 @@ def main():
     ap.add_argument("--workload", default=MAIN, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-frames", type=int, default=400)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-zero-copy", default=os.environ.get("WMD_E2E_ZERO_COPY", "0;0,1,2"),
+    ap.add_argument("--e2e-zero-copy", default=os.environ.get("WMD_E2E_ZERO_COPY", "0;0,1;0,1,2"),
                     help="';'-separated variants, each a comma list of skip-map indices that the variant leaves in pinned "
                          "host memory for the gated layout move to read in place (default: the finest map, then all three "
                          "sparse levels' maps); the fastest variant is reported as e2e; 'off' skips them")

@@ -180,6 +180,9 @@ typedef struct wmd_conv_desc {
   int32_t ldy;
   int32_t act;              /* WMD_ACT_* */
   float act_param;          /* LeakyReLU slope */
+  const int32_t* map1;      /* (N,H,W): row of pixel q in x1, -1 = none; NULL = x1 is dense (row q).  With a map, x1 holds
+                               only the rows of the listed pixels (sparse_upsample's skip[mask], KITTI/layers.py:500, kept
+                               compact: wmd_gather_rows_list_f32) */
   int32_t rows0;            /* rows allocated in x0, 0 = unknown.  Only used by the tensor-core engine's 1x1 form (taps == 1,
                                map0 == NULL: output row m reads x0 row m): with rows0 > 0 it loads whole 256-row tiles by TMA
                                (reads past rows0 are zero-filled) instead of gathering row by row */
@@ -295,6 +298,12 @@ typedef struct wmd_head_idwt_desc {
 int wmd_idwt_haar_epi_f32(const float* ll, const float* hf, float* out, float* disp, float disp_scale, int clamp01,
                           int epi_mode, float epi_a, float epi_b, float epi_lo, float epi_hi, float* epi_out0,
                           float* epi_out1, int N, int C, int H, int W, wmd_stream_t stream);
+/* rows[m][0..C) = src[n, :, y, x] for the m-th pixel of a list (pixels[m] = (n*H + y)*W + x, m < *count), columns C..ld-1
+ * zero: the layout move of a skip map restricted to EXACTLY the active pixels (the reference's skip[mask],
+ * KITTI/layers.py:500) - 128 list entries x 32 channels per tile, coalesced on both sides for clustered lists.  `src` may
+ * be pinned HOST memory (read in place over PCIe: only the listed pixels cross the bus).  ld % 4 == 0. */
+int wmd_gather_rows_list_f32(const float* src_nchw, float* rows, int ld, int C, const int32_t* pixels, const int32_t* count,
+                             int max_rows, int N, int H, int W, wmd_stream_t stream);
 size_t wmd_head_idwt_ws_bytes(int N, int H, int W);
 int wmd_head_idwt_f32(const wmd_head_idwt_desc* d, void* ws, size_t ws_bytes, wmd_stream_t stream);
 

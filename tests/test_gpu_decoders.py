@@ -325,6 +325,7 @@ def test_layout_move_options_are_bit_identical_eager_and_graphed():
     from wavelet_monodepth_b200 import graphs
     mod, _, feats = _full_kitti(synth.RESNET18_CH, 3, 192, 640)
     mod.overlap_layout = mod.gated_layout = False
+    mod.compact_skip = False                                 # these options concern the dense-row layout of the skip maps
     for thr in (0.05, 0.2, 0.4, 0.6, 0.8):                   # first threshold at which the gate really removes rows
         want = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in mod(feats, thr).items()}
         dens = float(want[("upsample_mask", 0)].float().mean())
@@ -582,3 +583,36 @@ def test_cold_first_launch_equals_warm_launches_in_a_fresh_process():
                          text=True, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "done" in res.stdout and "DIFF" not in res.stdout and "shape" not in res.stdout, res.stdout[-3000:]
+
+
+def test_compact_skip_rows_bit_identical_to_dense_skip_rows_device_and_pinned_host():
+    """compact_skip: a sparse level moves only the rows of its upsample mask out of the NCHW skip map (list-based
+    gather, wmd_gather_rows_list_f32) and upconv(i,1) reads them through S3's index map (wmd_conv_desc.map1) - same
+    values in the same MMAs as the dense row layout: every output must be bit-identical, eager and graphed, with the skip
+    maps on the device or in pinned host memory (read in place)."""
+    from wavelet_monodepth_b200 import graphs
+    mod = kd.SparseDepthWaveProgressiveDecoder(np.array(synth.RESNET18_CH))
+    synth.bench_kitti_params(mod)                            # the bench workload: clustered masks, 7-30 % dense
+    mod = mod.to(DEV).eval()
+    feats = [f.to(DEV) for f in synth.bench_kitti_features(3, 192, 640, synth.RESNET18_CH)]
+    mod.compact_skip = False
+    want = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in mod(feats, 0.05).items()}
+    assert 0.0 < float(want[("upsample_mask", 0)].float().mean()) < 0.9
+    mod.compact_skip = True
+    mod.compact_skip_levels = (1, 2, 3)
+    on_host = [f.cpu().pin_memory() for f in feats[:3]] + list(feats[3:])
+    for inputs in (feats, on_host):
+        for overlap in (True, False):
+            mod.overlap_compaction = overlap
+            got = mod(inputs, 0.05)
+            torch.cuda.synchronize()
+            for k, v in want.items():
+                assert (torch.equal(got[k], v) if torch.is_tensor(v) else got[k] == v), (inputs is on_host, overlap, key_str(k))
+        mod.overlap_compaction = True
+        g = graphs.GraphedSparseDecoder(mod, inputs, 0.05)
+        got = g.replay()
+        for k, v in want.items():
+            assert (torch.equal(got[k], v) if torch.is_tensor(v) else got[k] == v), ("graph", inputs is on_host, key_str(k))
+        del g
+    with pytest.raises(kd.WmdError):                       # the dense level's skip map must be on the device
+        mod(list(feats[:3]) + [feats[3].cpu().pin_memory(), feats[4]], 0.05)

@@ -477,3 +477,16 @@ def test_shared_tap_gather_is_bit_identical_to_per_tap_gather(case):
     for o in outs[1:]:
         assert torch.equal(o[:rows, :cout], outs[0][:rows, :cout])
     assert float(outs[0][:rows].abs().max()) > 0
+
+
+@pytest.mark.parametrize("n,c,h,w,p", [(2, 64, 12, 40, 0.3), (1, 5, 7, 9, 0.5), (3, 96, 16, 128, 0.02), (2, 32, 8, 64, 0.0), (2, 130, 9, 33, 1.0)])
+def test_gather_rows_list_matches_indexing(n, c, h, w, p):
+    x = rnd(n, c, h, w, seed=90)
+    mask = _blob_mask(n, h, w, p, 91, 1).to(DEV) if 0 < p < 1 else torch.full((n, 1, h, w), int(p), dtype=torch.uint8, device=DEV)
+    _, pixels, offsets = ops.compact(mask, want_idxmap=False)
+    m = int(offsets[n])
+    want = x.permute(0, 2, 3, 1).reshape(n * h * w, c)[mask.reshape(-1).bool().cpu()]
+    for src in (x.to(DEV), x.pin_memory()):
+        rows = ops.gather_rows_list(src, pixels, offsets[n:])
+        assert torch.equal(rows[:m, :c].cpu(), want)
+        assert rows.shape[1] == ops.pad4(c) and bool((rows[:m, c:] == 0).all())

@@ -32,6 +32,7 @@ class ConvDesc(Structure):
         ("pixels", c_void_p), ("count", c_void_p), ("max_rows", c_int32),
         ("y", c_void_p), ("ldy", c_int32),
         ("act", c_int32), ("act_param", c_float),
+        ("map1", c_void_p),
         ("rows0", c_int32),
     ]
 
@@ -92,6 +93,8 @@ SIGNATURES = {
     "wmd_nchw_to_rows_gated_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "wmd_rows_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "wmd_gather_rows_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_void_p]),
+    "wmd_gather_rows_list_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                          c_int, c_void_p]),
     "wmd_scatter_rows_nchw_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                           c_int, c_void_p]),

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) conv_rows_kernel(const wmd_co
           const int q = (n * d.H + qy) * d.W + qx;
           if (d.gate && !d.gate[q]) ok = false;
           if (ok) {
-            r1 = q;
+            r1 = d.map1 ? d.map1[q] : q;
             if (aligned_rows) {
               r0 = m;
             } else {

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
             const int q = (n * d.H + qy) * d.W + qx;
             if (d.gate && !d.gate[q]) ok = false;
             if (ok) {
-              o1 = q;
+              o1 = d.map1 ? d.map1[q] : q;          // -1 (not in the compact skip list) = kNoRow
               int r0;
               if (aligned_rows) {
                 r0 = m;

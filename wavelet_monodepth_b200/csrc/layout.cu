@@ -136,6 +136,60 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   }
 }
 
+// rows[m][c] = src[n, c, y, x] for the m-th listed pixel, at streaming speed for clustered lists.  Tile = 128 list entries
+// x 32 channels (the shape of nchw_to_rows): the plane offsets of the 128 pixels are decoded once into shared memory; a
+// warp then reads one channel of the 128 pixels as four requests (consecutive list entries are mostly consecutive pixels:
+// 128-byte requests inside a run) and the write side covers each row's 32 channels with eight float4 lanes (one full
+// 128-byte line per row).  Columns C..ld-1 are zero-filled.  src may be pinned host memory.
+__global__ void __launch_bounds__(256) gather_rows_list_kernel(const float* __restrict__ src, float* __restrict__ rows,
+                                                               int ld, int C, const int32_t* __restrict__ pixels,
+                                                               const int32_t* __restrict__ count, int max_rows,
+                                                               unsigned HW) {
+  __shared__ float tile[kTT][kTP + 1];
+  __shared__ long long base[kTP];                              // (n*C)*HW + yx of the tile's pixels, -1 past the list
+  const int M = count ? min(*count, max_rows) : max_rows;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ctiles = (ld + kTT - 1) / kTT;
+  const long long tiles = static_cast<long long>((M + kTP - 1) / kTP) * ctiles;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int m0 = static_cast<int>(t / ctiles) * kTP;
+    const int c0 = static_cast<int>(t % ctiles) * kTT;
+    if (threadIdx.x < kTP) {
+      const int mm = m0 + static_cast<int>(threadIdx.x);
+      long long b = -1;
+      if (mm < M) {
+        const unsigned p = static_cast<unsigned>(pixels ? pixels[mm] : mm);
+        const unsigned n = p / HW;
+        b = static_cast<long long>(n) * C * HW + (p - n * HW);
+      }
+      base[threadIdx.x] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = warp; r < kTT; r += 8) {
+      const int c = c0 + r;
+      const long long coff = static_cast<long long>(c) * HW;
+#pragma unroll
+      for (int j = 0; j < kTP / 32; ++j) {
+        const long long b = base[lane + 32 * j];
+        tile[r][lane + 32 * j] = (c < C && b >= 0) ? __ldg(src + b + coff) : 0.f;
+      }
+    }
+    __syncthreads();
+    const int q = lane & 7;
+#pragma unroll
+    for (int it = 0; it < kTP / 32; ++it) {
+      const int pl = it * 32 + warp * 4 + (lane >> 3);
+      const int m = m0 + pl;
+      const int c = c0 + 4 * q;
+      if (m < M && c < ld)
+        *reinterpret_cast<float4*>(rows + static_cast<long long>(m) * ld + c) =
+            make_float4(tile[4 * q][pl], tile[4 * q + 1][pl], tile[4 * q + 2][pl], tile[4 * q + 3][pl]);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ rows, int ld, int C,
                                                            const int32_t* __restrict__ pixels,
                                                            const int32_t* __restrict__ count, int max_rows,
@@ -233,6 +287,21 @@ extern "C" int wmd_gather_rows_nchw_f32(const float* src_nchw, float* rows, int 
   const long long tiles = static_cast<long long>(ceil_div(max_rows, kTT)) * ceil_div(C, kTT);
   gather_rows_kernel<<<stride_grid(tiles * 256, 256, 4), 256, 0, as_stream(stream)>>>(
       src_nchw, rows, ld, C, pixels, count, max_rows, static_cast<long long>(H) * W);
+  return launched();
+}
+
+extern "C" int wmd_gather_rows_list_f32(const float* src_nchw, float* rows, int ld, int C, const int32_t* pixels,
+                                        const int32_t* count, int max_rows, int N, int H, int W, wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(src_nchw && rows, WMD_ERR_ARG);
+  WMD_REQUIRE((pixels == nullptr) == (count == nullptr), WMD_ERR_ARG);
+  WMD_REQUIRE(C > 0 && ld >= C && ld % 4 == 0 && N >= 0 && H > 0 && W > 0 && max_rows >= 0, WMD_ERR_SHAPE);
+  WMD_REQUIRE((reinterpret_cast<uintptr_t>(rows) & 15) == 0, WMD_ERR_SHAPE);
+  WMD_REQUIRE(static_cast<long long>(N) * H * W < (1ll << 31), WMD_ERR_SHAPE);
+  if (max_rows == 0 || N == 0) return WMD_OK;
+  const long long tiles = static_cast<long long>(ceil_div(max_rows, kTP)) * ceil_div(ld, kTT);
+  gather_rows_list_kernel<<<stride_grid(tiles * 256, 256, 6), 256, 0, as_stream(stream)>>>(
+      src_nchw, rows, ld, C, pixels, count, max_rows, static_cast<unsigned>(static_cast<long long>(H) * W));
   return launched();
 }
 

@@ -173,6 +173,14 @@ class _WaveDecoderBase(nn.Module):
         self.factored_ll = os.environ.get("WMD_FACTORED_LL", "1") == "1"
         # compactions of the level's three active sets on parallel streams (WMD_OVERLAP_COMPACTION=0/1)
         self.overlap_compaction = os.environ.get("WMD_OVERLAP_COMPACTION", "1") == "1"
+        # sparse levels keep their skip map COMPACT: only the rows of the upsample mask S3 are moved out of the NCHW map
+        # (list-based gather-transpose: bytes scale with the mask density, 16-50 % on the bench) and upconv(i,1) reaches them
+        # through S3's index map (wmd_conv_desc.map1).  The skip map may then be a pinned HOST tensor.  WMD_COMPACT_SKIP=0/1
+        self.compact_skip = os.environ.get("WMD_COMPACT_SKIP", "1") == "1"
+        # ... at the levels where it pays on a device-resident map: measured (scripts/probe_gather.py, B200) the list-based
+        # gather moves ~2 TB/s of useful bytes against 6.5 TB/s for the whole-map transpose, so it wins below ~30 % mask
+        # density - levels 2 and 1 (16-28 % on the bench), not level 3 (50 %).  A pinned-host skip map always takes it.
+        self.compact_skip_levels = (1, 2)
         # tail of every level as one kernel: head gather-sum -> yh -> IDWT -> disp -> next level's threshold
         # (wmd_head_idwt_f32; WMD_FUSED_TAIL=0/1).  Bit-identical to the head_gather + idwt_haar + range_thresh chain.
         self.fused_tail = os.environ.get("WMD_FUSED_TAIL", "1") == "1"
@@ -282,7 +290,7 @@ class _WaveDecoderBase(nn.Module):
 
     def _native_forward_on_device(self, feats, thresh_ratio, sparse_levels, with_masks):
         # with gated_layout the skip map of a sparse level i (feats[i-1]) may live in pinned host memory
-        _need_cuda(feats, host_ok=tuple(i - 1 for i in sparse_levels) if self.gated_layout else ())
+        _need_cuda(feats, host_ok=tuple(i - 1 for i in sparse_levels) if (self.gated_layout or self.compact_skip) else ())
         out = {}
         n = feats[-1].shape[0]
         dev = feats[-1].device
@@ -315,7 +323,18 @@ class _WaveDecoderBase(nn.Module):
                     masks = ops.level_masks(yh, thresh)
             skip_gate = masks["S3"] if (sparse and self.gated_layout) else None
             skip_done = None
-            if side is not None:
+            map3 = None
+            if sparse and self.compact_skip and (i in self.compact_skip_levels or not skip.is_cuda) and \
+                    ops.rows_view(skip) is None:                         # channels_last maps are used in place instead
+                # S3's compaction and the gather of exactly its rows, on a side stream next to gate_map / compact(S2) / upconv(i,0)
+                s3 = _side_stream(dev, 3) if self.overlap_compaction else None
+                if s3 is not None:
+                    (map3, pix3, off3), _ = ops.compact(masks["S3"], stream=s3, ws_slot=3)
+                    skip_rows, skip_done = ops.gather_rows_list(skip, pix3, off3[n:], stream=s3)
+                else:
+                    map3, pix3, off3 = ops.compact(masks["S3"], ws_slot=3)
+                    skip_rows = ops.gather_rows_list(skip, pix3, off3[n:])
+            elif side is not None:
                 skip_rows, skip_done = ops.nchw_to_rows(skip, stream=side, gate=skip_gate)
             else:
                 skip_rows = ops.nchw_to_rows(skip, gate=skip_gate)
@@ -352,7 +371,7 @@ class _WaveDecoderBase(nn.Module):
                     torch.cuda.current_stream(dev).wait_event(ev4)
                     torch.cuda.current_stream(dev).wait_event(ev5)
                 xb = ops.conv_rows(xa, c, wp1, b1, c, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_ELU, map0=map2,
-                                   shift0=1, x1=skip_rows, c1=cs, gate=masks["S3"], pixels=pix4, count=off4[n:],
+                                   shift0=1, x1=skip_rows, c1=cs, map1=map3, gate=masks["S3"], pixels=pix4, count=off4[n:],
                                    m_in0=off2[n:], m_in1=_pm(lambda: masks["S3"].sum()))
                 if mlp is None:
                     t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1,

@@ -332,6 +332,16 @@ def pad4(c):
     return (int(c) + 3) // 4 * 4
 
 
+def rows_view(x):
+    """The zero-copy pixel-major rows of a channels_last feature map ((N*H*W, C) view), or None if x is not laid out so."""
+    if not x.is_cuda or x.dtype != _f32 or x.dim() != 4:
+        return None
+    n, c, h, w = x.shape
+    if c % 4 == 0 and x.permute(0, 2, 3, 1).is_contiguous() and x.data_ptr() % 16 == 0:
+        return x.permute(0, 2, 3, 1).reshape(n * h * w, c)
+    return None
+
+
 @_on_device
 def nchw_to_rows(x, ld=None, stream=None, gate=None):
     """(N,C,H,W) -> rows (N*H*W, ld) pixel-major.  Zero-copy when x is channels_last and C % 4 == 0.
@@ -420,6 +430,42 @@ def gather_rows(x_nchw, pixels, count, max_rows=None, ld=None):
 
 
 @_on_device
+def gather_rows_list(x, pixels, count, ld=None, stream=None):
+    """Compact rows of the listed pixels of an NCHW map: rows[m] = x[n, :, y, x] for pixels[m] (wmd_gather_rows_list_f32).
+
+    x: (N,C,H,W) CUDA tensor or PINNED HOST tensor (read in place over PCIe: only the listed pixels cross the bus).
+    pixels / count: list + device count from `compact`.  Returns rows (N*H*W capacity, ld); rows past *count are
+    uninitialised.  stream: as in nchw_to_rows (side stream; returns (rows, event))."""
+    lib = _lib.load()
+    n, c, h, w = x.shape
+    ld = pad4(c) if ld is None else ld
+    on_host = not x.is_cuda
+    dev = pixels.device
+    if on_host:
+        if x.dtype != _f32 or not x.is_contiguous() or x.data_ptr() % 16:
+            raise _lib.WmdError("gather_rows_list: host feature maps must be contiguous fp32 NCHW, 16-byte aligned")
+    else:
+        x = _dense(x)
+    rows = torch.empty((max(n * h * w, 1), ld), dtype=_f32, device=dev)
+
+    def launch():
+        with _prof('gather_rows_list', lambda: dict(c=c, ld=ld, count=count, max_rows=n * h * w, host=on_host)):
+            rc = lib.wmd_gather_rows_list_f32(_lib.host_ptr(x, _f32), _lib.ptr(rows), ld, c, _lib.ptr(pixels, _i32),
+                                              _lib.ptr(count, _i32), n * h * w, n, h, w, _lib.stream_ptr())
+        _lib.check(rc, "wmd_gather_rows_list_f32")
+
+    if stream is None:
+        launch()
+        return rows
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(stream):
+        launch()
+        done = torch.cuda.Event()
+        done.record(stream)
+    return rows, done
+
+
+@_on_device
 def scatter_rows(rows, c, pixels, count, n, h, w, max_rows=None, out=None):
     """Dense (N,C,H,W), zero except at the listed pixels where it takes rows[m, :c]."""
     lib = _lib.load()
@@ -502,7 +548,7 @@ def pack_weight(weight, c1=0, kind=None):
 @_on_device
 def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act=ACT_NONE, act_param=0.0,
               map0=None, shift0=0, x1=None, c1=0, gate=None, pixels=None, count=None, max_rows=None, out=None,
-              m_in0=None, m_in1=None, splits=None):
+              m_in0=None, m_in1=None, splits=None, map1=None):
     """Gather-GEMM convolution on pixel-major rows; see wmd_conv_rows_f32 in include/wmd.h.
 
     m_in0 / m_in1: optional active-row counts of the two sources (ints or 1-element device tensors), used only
@@ -526,6 +572,7 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
     d.map0, d.shift0 = _lib.ptr(map0, _i32), shift0
     d.x1, d.c1, d.ld1 = (_lib.ptr(x1, _f32), c1, x1.shape[1]) if x1 is not None else (None, 0, 0)
     d.gate = _lib.ptr(gate, _u8)
+    d.map1 = _lib.ptr(map1, _i32) if x1 is not None else None
     d.w, d.bias = _lib.ptr(wpacked.data, _f32), _lib.ptr(bias, _f32)
     d.cout, d.ldw, d.taps, d.pad_mode = cout, (wpacked.data.shape[1] if wpacked.kind == "simt" else 0), taps, pad
     d.pixels, d.count, d.max_rows = _lib.ptr(pixels, _i32), _lib.ptr(count, _i32), max_rows
