@@ -261,7 +261,7 @@ def roofline_from(records, peak_gbs, peak_tf, peak_src, steps, peak_tf_sustained
                 "peak_alternatives": {"tf32_measured_here_tflops": round(tf32_peak, 1) if tf32_peak else None,
                                       "bf16_burst_over_2": round(peak_tf / 2.0, 1),
                                       "bf16_sustained_over_2": round(peak_tf_sustained / 2.0, 1) if peak_tf_sustained else None},
-                "peak_source": ("measured in this run: cuBLAS TF32 GEMM 8192^3, best of 10 (burst; each launch is timed alone "
+                "peak_source": ("measured in this run: cuBLAS TF32 GEMM 8192^3, best of 20 (burst; each launch is timed alone "
                                 "between two events)" if tf32_peak else peak_src + ": bf16_tflops / 2"),
                 "note": "achieved = algorithmic fp32-equivalent flops (2*taps*Cin*Cout*M_out) / event time. tcgen05.mma.kind::tf32, "
                         "3 MMAs per fp32 product (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM drained every 1024 of K; "
@@ -492,17 +492,17 @@ def time_device(step_fn, steps, warmup, dist, world, flush=None):
 
 def measure_tf32_peak(dev):
     """Dense TF32 tensor-core throughput of this GPU, measured the way MEASURED_PEAKS.json measures bf16: cuBLAS GEMM
-    8192^3 (fp32 operands, allow_tf32), best of 10, CUDA events."""
+    8192^3 (fp32 operands, allow_tf32), best of 20 after 10 warm-up launches, CUDA events."""
     was = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
         n = 8192
         a = torch.randn(n, n, device=dev)
         b = torch.randn(n, n, device=dev)
-        for _ in range(3):
+        for _ in range(10):                   # clocks ramp over the first launches
             torch.matmul(a, b)
         best = None
-        for _ in range(10):
+        for _ in range(20):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             torch.matmul(a, b)

@@ -20,8 +20,9 @@ for r in csv.DictReader(io.StringIO(text)):
         rows.append((r["Kernel Name"], float(r["Metric Value"])))
 # profile_step.py ran 2 decoder steps; keep the second (weights packed, allocator warm).  A step starts with the layout
 # move of the coarsest feature map and has five of them: the second step starts at the sixth nchw_to_rows launch.
+# (the number of whole-map moves per step depends on the layout options: take the second half of them)
 moves = [i for i, (name, _) in enumerate(rows) if "nchw_to_rows" in name]
-step = rows[moves[5]:] if len(moves) >= 10 else rows[len(rows) // 2:]
+step = rows[moves[len(moves) // 2]:] if len(moves) >= 2 and len(moves) % 2 == 0 else rows[len(rows) // 2:]
 agg = {}
 for name, ns in step:
     short = name.split("(")[0].replace("void ", "").replace("wmd::", "")
@@ -83,19 +84,20 @@ if os.path.exists(other):
     hdr, units, data = rd[0], rd[1], rd[2:]
     idx = [hdr.index(w) for w in want if w in hdr]
     with open(os.path.join(out_dir, "%s_idwt_layout_ncu_full.csv" % tag), "w") as f:
-        f.write("# %s: ncu --set full --clock-control none --import-source on -k regex:'head_idwt|nchw_to_rows' -s 9 -c 9 python "
+        f.write("# %s: ncu --set full --clock-control none --import-source on -k regex:'head_idwt|nchw_to_rows|gather_rows_list' -s 9 -c 9 python "
                 "scripts/profile_step.py 2 (second decoder step, R50 1024x320 bs32): head_idwt = fused level tail (head gather-sum -> "
-                "yh -> IDWT -> disp -> next threshold), nchw_to_rows = layout moves of the encoder maps\n" % tag)
+                "yh -> IDWT -> disp -> next threshold), nchw_to_rows = whole-map layout moves (dense level), gather_rows_list = "
+                "compact skip rows of the sparse levels\n" % tag)
         w = csv.writer(f)
         w.writerow([hdr[i] for i in idx])
         w.writerow([units[i] for i in idx])
         for r in data:
             w.writerow([r[i] for i in idx])
     ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
-    for key in ("head_idwt", "nchw_to_rows"):
+    for key in ("head_idwt", "nchw_to_rows", "gather_rows_list"):
         v = [to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in data if key in r[it]]
         if v:
             tj[key] = int(sum(v) / len(v))
     tj["source_other"] = "profiles/%s_idwt_layout_ncu_full.csv (mean dram read+write per launch)" % tag
     json.dump(tj, open(traffic_path, "w"))
-    print("second capture:", len(data), "launches;", {k: tj.get(k) for k in ("head_idwt", "nchw_to_rows")})
+    print("second capture:", len(data), "launches;", {k: tj.get(k) for k in ("head_idwt", "nchw_to_rows", "gather_rows_list")})
