@@ -134,3 +134,38 @@ def test_sparse_scales_subsets_vs_oracle(sparse_scales):
     sparse, sd = _bench_decoder(kd.SparseDepthWaveProgressiveDecoder, ch)
     out = sparse([f.to(DEV) for f in feats], 0.05, sparse_scales=list(sparse_scales))
     _check_batch(out, feats, sd, 0.05, sparse_scales=sparse_scales, what="R18 sparse_scales=%s" % (sparse_scales,))
+
+
+@pytest.mark.parametrize("thr", [0.1, 0.0])
+def test_config3_nyu_densenet161_640x480_bs8_vs_per_sample_oracle(thr):
+    """configs[3]: DenseNet161 pyramid 640x480, batch 8, SparseDecoderWave - the bench's NYU workload (high-pass wave heads,
+    blocky features) against oracle.nyu.sparse_forward run per sample (the reference's mask2idxmap asserts batch 1)."""
+    from oracle import nyu as onyu
+    from wavelet_monodepth_b200 import nyu_decoders as nd
+    heads = ["wave1.conv.", "wave2.conv.", "wave3.conv."]
+    mod = nd.SparseDecoderWave(enc_features=list(synth.DENSENET161_CH), decoder_width=0.5)
+    sd = synth.load_random(mod, seed=11, gains={k: 4.0 for k in heads}, highpass=heads)
+    mod = mod.to(DEV).eval()
+    n = 8
+    feats = synth.blocky_features(synth.nyu_feature_shapes(n, 480, 640, synth.DENSENET161_CH), seed=2000, cell=16, texture=0.01)
+    out = mod([f.to(DEV) for f in feats], thr)
+    worst = 0.0
+    with torch.no_grad():
+        for b in range(n):
+            ref = onyu.sparse_forward(sd, [f[b:b + 1] for f in feats], thr)
+            assert out["total_ops_per_sample"][b] == ref["total_ops"], b
+            for k, v in ref.items():
+                if k == "total_ops":
+                    continue
+                g = out[k][b:b + 1].cpu()
+                if k[0] == "wavelet_mask":
+                    assert torch.equal(g.bool(), v.bool()), (b, k)
+                else:
+                    e = parity.rel_err(g, v)
+                    worst = max(worst, e)
+                    assert e <= REL_TOL, (b, k, e)
+    print("[parity] N161 640x480 bs8 thr=%g: max rel err %.3e, masks exact, total_ops exact" % (thr, worst))
+    if thr == 0.0:
+        assert out["total_ops_per_sample"] == [33463546800] * n                # NYUv2/sparsity_test_notebook.ipynb:1344
+    else:
+        assert float(out[("wavelet_mask", 0)].float().mean()) < 0.5
