@@ -183,6 +183,14 @@ typedef struct wmd_conv_desc {
   const int32_t* map1;      /* (N,H,W): row of pixel q in x1, -1 = none; NULL = x1 is dense (row q).  With a map, x1 holds
                                only the rows of the listed pixels (sparse_upsample's skip[mask], KITTI/layers.py:500, kept
                                compact: wmd_gather_rows_list_f32) */
+  int32_t precision;        /* tensor-core engine only.  0 = WMD_PREC_TF32X3: operands split into tf32 hi + lo.  1 = WMD_PREC_F16X3:
+                               operands split into two fp16 pieces of x * 2^k (same 22 mantissa bits; k from amax0 / amax1, so
+                               nothing overflows) - half the MMA instructions and twice their rate; needs amax0 (and amax1 when
+                               c1 > 0) and weights packed by wmd_pack_conv_weight_tc16_f32 */
+  const float* amax0;       /* device scalars: max |x0|, max |x1| over the rows the launch can read (upper bounds are fine) */
+  const float* amax1;
+  float* amax_out;          /* device scalar, or NULL: atomically raised to max |y| of the rows written (zero it before the
+                               first producer; both precisions) */
   int32_t rows0;            /* rows allocated in x0, 0 = unknown.  Only used by the tensor-core engine's 1x1 form (taps == 1,
                                map0 == NULL: output row m reads x0 row m): with rows0 > 0 it loads whole 256-row tiles by TMA
                                (reads past rows0 are zero-filled) instead of gathering row by row */
@@ -199,7 +207,19 @@ int wmd_conv_rows_f32(const wmd_conv_desc* d, wmd_stream_t stream);
  *                                            shared-memory images [tf32 hi | tf32 lo] of N x 32, K-major, 128-byte swizzled
  * Accumulation runs in epochs of K = 1024 inside TMEM and is drained into fp32 registers with round-to-nearest
  * adds, because the tensor core's own fp32 accumulation rounds toward zero (bias ~6.5e-9 * K relative). */
+enum { WMD_PREC_TF32X3 = 0, WMD_PREC_F16X3 = 1 };
 int wmd_conv_tc_tile_n(int cout);
+/* Weights for precision = WMD_PREC_F16X3: 128-byte header (float 0: 1 / s_w) + per (n-tile, 32-channel chunk) one N x 128 B
+ * image whose rows hold [fp16(w s_w): 32 channels | fp16(w s_w - that): 32 channels], s_w = the power of two that puts
+ * max |w| into (2^13, 2^14] (computed on the device, no host sync).  `packed` needs wmd_conv_tc16_weight_bytes() bytes. */
+size_t wmd_conv_tc16_weight_bytes(int cout, int c0, int c1, int taps);
+int wmd_pack_conv_weight_tc16_f32(const float* w, void* packed, int Cout, int c0, int c1, int taps, wmd_stream_t stream);
+/* max |x| of `count` floats, atomically raised into *amax (device scalar, zero it first): for sources that no libwmd
+ * kernel produced (channels_last feature maps used in place).  The layout moves below take an optional `amax` too. */
+int wmd_amax_f32(const float* x, long long count, float* amax, wmd_stream_t stream);
+int wmd_nchw_to_rows_amax_f32(const float* src, float* dst, int N, int C, long long HW, int ld, float* amax, wmd_stream_t stream);
+int wmd_gather_rows_list_amax_f32(const float* src_nchw, float* rows, int ld, int C, const int32_t* pixels,
+                                  const int32_t* count, int max_rows, int N, int H, int W, float* amax, wmd_stream_t stream);
 size_t wmd_conv_tc_weight_floats(int cout, int c0, int c1, int taps);
 int wmd_pack_conv_weight_tc_f32(const float* w, float* packed, int Cout, int c0, int c1, int taps, wmd_stream_t stream);
 int wmd_conv_rows_tc_f32(const wmd_conv_desc* d, wmd_stream_t stream);

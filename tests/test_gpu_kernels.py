@@ -490,3 +490,30 @@ def test_gather_rows_list_matches_indexing(n, c, h, w, p):
         rows = ops.gather_rows_list(src, pixels, offsets[n:])
         assert torch.equal(rows[:m, :c].cpu(), want)
         assert rows.shape[1] == ops.pad4(c) and bool((rows[:m, c:] == 0).all())
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-3, 3e4])
+@pytest.mark.parametrize("n,cin,c1,cout,h,w", [(2, 64, 0, 32, 12, 20), (1, 96, 32, 64, 9, 11), (2, 40, 0, 128, 6, 10), (2, 256, 64, 256, 8, 12)])
+def test_f16x3_conv_matches_fp64_reference_across_magnitudes(n, cin, c1, cout, h, w, scale):
+    """precision = f16x3: operands fed as fp16 pairs of power-of-two scaled values (scale from the sources' max |x|, weights'
+    scale in the packed header), fp32 accumulation - as accurate as the tf32 hi/lo form whatever the magnitude of the
+    activations (1e-3 .. 3e4: far outside fp16's own range without the scaling)."""
+    c0 = cin - c1
+    x0 = rnd(n, c0, h, w, seed=80) * scale
+    x1 = rnd(n, c1, h, w, seed=81) * scale * 0.25 if c1 else None
+    wt, b = rnd(cout, cin, 3, 3, seed=82, lo=-0.1, hi=0.1), rnd(cout, seed=83) * scale
+    xin = torch.cat([x0, x1], 1) if c1 else x0
+    want = F.elu(F.conv2d(F.pad(xin.double(), (1, 1, 1, 1), mode="reflect"), wt.double(), b.double())).float()
+    wp = ops.pack_weight(wt.to(DEV), c1, kind="tc", precision="f16x3")
+    assert wp.data16 is not None
+    am = torch.zeros(3, device=DEV)
+    r0 = ops.nchw_to_rows(x0.to(DEV), amax=am[0:1])
+    r1 = ops.nchw_to_rows(x1.to(DEV), amax=am[1:2]) if c1 else None
+    assert float(am[0]) == float(x0.abs().max())
+    kw = dict(pad=PAD_REFLECT, act=ACT_ELU, x1=r1, c1=c1)
+    y16 = ops.conv_rows(r0, c0, wp, b.to(DEV), cout, n, h, w, amax0=am[0:1], amax1=am[1:2] if c1 else None, amax_out=am[2:3], **kw)
+    y32 = ops.conv_rows(r0, c0, wp, b.to(DEV), cout, n, h, w, **kw)
+    got16, got32 = ops.rows_to_nchw(y16, n, cout, h, w), ops.rows_to_nchw(y32, n, cout, h, w)
+    e16, e32 = rel_err(got16, want), rel_err(got32, want)
+    assert e16 <= 1e-5 and e16 <= 2 * e32 + 1e-6, (e16, e32)        # both carry the truncating accumulation's bias
+    assert abs(float(am[2]) - float(got16.abs().max())) <= 1e-6 * float(got16.abs().max())

@@ -33,6 +33,7 @@ class ConvDesc(Structure):
         ("y", c_void_p), ("ldy", c_int32),
         ("act", c_int32), ("act_param", c_float),
         ("map1", c_void_p),
+        ("precision", c_int32), ("amax0", c_void_p), ("amax1", c_void_p), ("amax_out", c_void_p),
         ("rows0", c_int32),
     ]
 
@@ -66,6 +67,7 @@ class HeadIdwtDesc(Structure):
 
 
 EPI_NONE, EPI_DISP_TO_DEPTH, EPI_DIV_CLAMP = 0, 1, 2
+PREC_TF32X3, PREC_F16X3 = 0, 1
 
 # name -> (restype, argtypes); must list every symbol include/wmd.h declares (tests/test_abi.py checks)
 SIGNATURES = {
@@ -106,6 +108,12 @@ SIGNATURES = {
                                  c_void_p]),
     "wmd_conv_rows_f32": (c_int, [POINTER(ConvDesc), c_void_p]),
     "wmd_conv_tc_tile_n": (c_int, [c_int]),
+    "wmd_conv_tc16_weight_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "wmd_pack_conv_weight_tc16_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "wmd_amax_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
+    "wmd_nchw_to_rows_amax_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p]),
+    "wmd_gather_rows_list_amax_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                              c_int, c_void_p, c_void_p]),
     "wmd_conv_tc_set_shared_taps": (c_int, [c_int]),
     "wmd_conv_tc_weight_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "wmd_pack_conv_weight_tc_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

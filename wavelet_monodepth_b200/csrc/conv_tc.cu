@@ -38,6 +38,7 @@
 // (source, dy)) falls back to one fill per chunk with identity slots - same code, group size 1.
 // TMEM map (512 columns): [0,2N) accumulators (half h at h*N), [256,512) A operand: stage s, half h at
 // 256 + s*128 + h*64, hi in the first 32 columns, lo in the next 32.
+#include <cuda_fp16.h>
 #include <cuda.h>   // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
 
 #include "common.cuh"
@@ -67,9 +68,12 @@ constexpr uint16_t kZeroSlot = 0xFFFFu;          // slot-table entry of a tap th
 
 // Per N-tile configuration.  Accumulators: M half h at TMEM column h*BN; each is written by exactly one issuer, so the
 // order of the round-toward-zero accumulations - and with it every output bit - is fixed.
-template <int BN, bool SH = false>
+template <int BN, bool SH = false, bool F16 = false>
 struct TcCfg {
-  static constexpr int B_TILE = BN * TC_BK * 4;            // bytes of one of hi / lo
+  static constexpr int B_TILE = BN * TC_BK * 4;            // bytes of one of hi / lo (tf32 form)
+  // weight image of one chunk: tf32 form [hi: BN x 128 B | lo: BN x 128 B]; f16 form ONE BN x 128 B tile whose rows hold
+  // [h1: 32 channels | h2: 32 channels] as fp16
+  static constexpr int B_IMG = F16 ? B_TILE : 2 * B_TILE;
   static constexpr int ACC = BN / 2;                       // accumulator registers per thread: its row x BN/2 columns
   static constexpr int A_BYTES = SH ? TC_SH_STAGES * TC_SH_TILE : TC_A_STAGES * TC_A_TILE;   // 96 KB either way
   // Pipeline depth.  The loop split(c) -> MMA(c) -> [TMEM stage free] -> split(c + T) and the weight prefetch
@@ -81,7 +85,7 @@ struct TcCfg {
   static constexpr int T_STAGES = BN <= 64 ? 3 : 2;
   static constexpr int B_STAGES = BN <= 64 ? 4 : 3;
   static constexpr uint32_t A_COL0 = 512u - T_STAGES * 128u;        // first TMEM column of the split A operand
-  static constexpr size_t SMEM = static_cast<size_t>(A_BYTES) + static_cast<size_t>(B_STAGES) * 2 * B_TILE + TC_TABLES +
+  static constexpr size_t SMEM = static_cast<size_t>(A_BYTES) + static_cast<size_t>(B_STAGES) * B_IMG + TC_TABLES +
                                  (SH ? TC_SH_TABLES : 0) + 1024;
   static_assert(2 * BN <= static_cast<int>(A_COL0), "accumulators must leave the A operand's TMEM columns free");
 };
@@ -161,6 +165,32 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
+}
+// same with fp16 operands (kind::f16): A is 128 lanes x 16 halves = 8 columns in tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// two floats -> packed fp16 pair, round to nearest even, saturating at +-65504 (a stray out-of-range value must not turn
+// into inf - inf = NaN in the remainder piece); `lo` lands in bits 0..15 (the lower K index)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t pair) {
+  float f;
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}\n" : "=f"(f) : "r"(pair));
+  return f;
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t pair) {
+  float f;
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}\n" : "=f"(f) : "r"(pair));
+  return f;
 }
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
@@ -245,13 +275,14 @@ __host__ __device__ __forceinline__ BalPlan bal_plan(long long tiles, long long 
   return p;
 }
 
-template <int BN, bool SH>
+template <int BN, bool SH, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_conv_desc d, const float* __restrict__ wtc,
                                                                      const int splits, float* __restrict__ partial,
                                                                      const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1) {
-  using Cfg = TcCfg<BN, SH>;
+  using Cfg = TcCfg<BN, SH, F16>;
   constexpr int TC_B_TILE = Cfg::B_TILE;
+  constexpr int B_IMG = Cfg::B_IMG;                         // bytes of one chunk's weight image
   constexpr int ACC = Cfg::ACC;
   constexpr int TC_T_STAGES = Cfg::T_STAGES;
   constexpr int TC_B_STAGES = Cfg::B_STAGES;
@@ -272,7 +303,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* sA_base = base;
   unsigned char* sB_base = base + Cfg::A_BYTES;
-  int32_t* tab0 = reinterpret_cast<int32_t*>(sB_base + TC_B_STAGES * 2 * TC_B_TILE);   // [tap][row]: source row in x0, -1 = none
+  int32_t* tab0 = reinterpret_cast<int32_t*>(sB_base + TC_B_STAGES * B_IMG);   // [tap][row]: source row in x0, -1 = none
   int32_t* tab1 = tab0 + 9 * TC_BM;                                                    // ... in x1
   // shared-tap gather tables (SH): extra source rows [src][dy][128], slots [src][dy][side][row], counters [src*3+dy], [6] = overflow
   int32_t* xtra = tab1 + 9 * TC_BM;
@@ -306,6 +337,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_slot;
 
+  // F16: operands are fed as fp16 pairs.  Activations are scaled by a power of two chosen from the sources' max |x| (device
+  // scalars written by their producers: layout moves, earlier convolutions) so that max |x| s lies in (2^13, 2^14] - no
+  // overflow, the low piece stays normal for everything within 2^-11 .. 1 of the maximum; weights carry their own
+  // power-of-two scale in the packed image's header.  Both scales are undone exactly in the epilogue.
+  float ascale = 1.f, out_scale = 1.f;
+  if (F16) {
+    float amax = d.amax0 ? __ldg(d.amax0) : 0.f;
+    if (d.c1 > 0 && d.amax1) amax = fmaxf(amax, __ldg(d.amax1));
+    int e = 0;
+    if (amax > 0.f && amax < INFINITY) {
+      int ex;
+      frexpf(amax, &ex);                         // amax = m * 2^ex, m in [0.5, 1)
+      e = 14 - ex;                               // amax * 2^e in [2^13, 2^14)
+    }
+    e = max(-100, min(100, e));
+    ascale = ldexpf(1.f, e);
+    out_scale = ldexpf(1.f, -e) * __ldg(wtc);    // header word 0: 1 / weight scale
+  }
   const long long HW = static_cast<long long>(d.H) * d.W;
   const int total_px = static_cast<int>(static_cast<long long>(d.N) * HW);
   int rows = d.pixels ? *d.count : total_px;
@@ -319,7 +368,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
   const bool aligned_rows = (d.taps == 1 && d.map0 == nullptr);
   const bool tiled_rows = aligned_rows && d.rows0 > 0;         // tm0 then has a 256-row box (launch_tc)
   // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
-  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+  // (F16: A = B = f16, format code 0, K = 16 per instruction)
+  constexpr uint32_t kFmt = F16 ? 0u : 2u;
+  constexpr uint32_t kIdesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                               (static_cast<uint32_t>(128 >> 4) << 24);
 
   // drain / store ownership (all 16 warps): TMEM lane quarter, M half, column half (ACC = BN/2 columns of every copy)
@@ -389,6 +440,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     const int m0 = static_cast<int>(tile / n_tiles) * TC_BM;
     const int nt = static_cast<int>(tile % n_tiles);
     const int n0 = nt * BN;
+    // rows / bias 16-byte aligned: the epilogue's vector form for the quads inside cout
+    const bool al_ok = (d.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0);
     TC_TILE_TRACE(0);
 
     if (SH) {                                      // extras default to "no row" (the tail of a 4-row load group), counters to 0
@@ -481,12 +535,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     TC_TILE_TRACE(1);
 
     const unsigned char* wtile = reinterpret_cast<const unsigned char*>(wtc) +
-                                 static_cast<long long>(nt) * nchunks * (2 * TC_B_TILE);
+                                 (F16 ? 128 : 0) + static_cast<long long>(nt) * nchunks * B_IMG;   // f16 images follow a 128-byte header
     const uint32_t round0 = mma_rounds;
 
     float acc[ACC];
 #pragma unroll
     for (int j = 0; j < ACC; ++j) acc[j] = 0.f;
+    float out_max = 0.f;                          // max |y| this thread stores in this tile (-> d.amax_out)
 
     // drains this thread's slice (its row, ACC columns of every issuer's copy) with round-to-nearest adds, re-zeroes it
     auto drain = [&]() {
@@ -677,25 +732,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         const uint32_t ta = tmem_acc + lane_field + Cfg::A_COL0 + ts * 128u + static_cast<uint32_t>(my_half * 64);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {              // 16 channels at a time
-          uint32_t hi[16], lo[16];
+          uint4 v4[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 v;
             if (kEarly) {
-              v = rawv[kEarly ? 4 * hf + q : 0];
+              v4[q] = rawv[kEarly ? 4 * hf + q : 0];
             } else {
-              v = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(4 * hf + q) ^ swz) << 4));
-              if (SH && zero_row) v = make_uint4(0u, 0u, 0u, 0u);
-            }
-            const uint32_t raw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              hi[4 * q + e] = raw[e] & 0xFFFFE000u;                                                    // tf32 by truncation
-              lo[4 * q + e] = __float_as_uint(__uint_as_float(raw[e]) - __uint_as_float(hi[4 * q + e]));   // exact remainder
+              v4[q] = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(4 * hf + q) ^ swz) << 4));
+              if (SH && zero_row) v4[q] = make_uint4(0u, 0u, 0u, 0u);
             }
           }
-          tmem_st16(ta + static_cast<uint32_t>(16 * hf), hi);
-          tmem_st16(ta + 32u + static_cast<uint32_t>(16 * hf), lo);
+          if (F16) {
+            // x * s (s a power of two: exact) = h1 + h2 with h1 = fp16(x s) and h2 = fp16(x s - h1): 22 mantissa bits, the
+            // precision of the tf32 hi / lo pair; two halves per 32-bit TMEM column, lower channel in the lower half
+            uint32_t h1[8], h2[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float b0 = __uint_as_float(v4[q].x) * ascale, b1 = __uint_as_float(v4[q].y) * ascale;
+              const float b2 = __uint_as_float(v4[q].z) * ascale, b3 = __uint_as_float(v4[q].w) * ascale;
+              const uint32_t p0 = pack_f16x2(b0, b1), p1 = pack_f16x2(b2, b3);
+              h1[2 * q] = p0;
+              h1[2 * q + 1] = p1;
+              h2[2 * q] = pack_f16x2(b0 - f16_lo_to_f32(p0), b1 - f16_hi_to_f32(p0));
+              h2[2 * q + 1] = pack_f16x2(b2 - f16_lo_to_f32(p1), b3 - f16_hi_to_f32(p1));
+            }
+            tmem_st8(ta + static_cast<uint32_t>(8 * hf), h1);
+            tmem_st8(ta + 16u + static_cast<uint32_t>(8 * hf), h2);
+          } else {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t raw[4] = {v4[q].x, v4[q].y, v4[q].z, v4[q].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hi[4 * q + e] = raw[e] & 0xFFFFE000u;                                                    // tf32 by truncation
+                lo[4 * q + e] = __float_as_uint(__uint_as_float(raw[e]) - __uint_as_float(hi[4 * q + e]));   // exact remainder
+              }
+            }
+            tmem_st16(ta + static_cast<uint32_t>(16 * hf), hi);
+            tmem_st16(ta + 32u + static_cast<uint32_t>(16 * hf), lo);
+          }
         }
         if (!kEarly) {
           __syncwarp();
@@ -759,10 +835,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       // the issuers' loop.
       const uint32_t sB_u = __shfl_sync(0xffffffffu, smem_u32(sB_base), 0);
       if (elect_one()) {
-        const unsigned char* w0 = wtile + static_cast<long long>(cb) * (2 * TC_B_TILE);
+        const unsigned char* w0 = wtile + static_cast<long long>(cb) * B_IMG;
         // the first B_STAGES - 1 weight images (their stages are free: every MMA of the previous tile has completed)
         for (int k = 0; k < TC_B_STAGES - 1 && k < len; ++k)
-          bulk_g2s(sB_u + ((round0 + k) % TC_B_STAGES) * 2 * TC_B_TILE, w0 + static_cast<long long>(k) * (2 * TC_B_TILE), 2 * TC_B_TILE,
+          bulk_g2s(sB_u + ((round0 + k) % TC_B_STAGES) * B_IMG, w0 + static_cast<long long>(k) * B_IMG, B_IMG,
                    smem_u32(&bar_b[(round0 + k) % TC_B_STAGES]));
       }
       __syncwarp();
@@ -774,8 +850,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           if (c >= 1) mbar_wait(smem_u32(&bar_bfree[(round - 1) % TC_B_STAGES]), ((round - 1) / TC_B_STAGES) & 1, 0x50000u + round);
           if (elect_one()) {
             const uint32_t ns = (round + TC_B_STAGES - 1) % TC_B_STAGES;
-            bulk_g2s(sB_u + ns * 2 * TC_B_TILE, wtile + static_cast<long long>(cb + c + TC_B_STAGES - 1) * (2 * TC_B_TILE),
-                     2 * TC_B_TILE, smem_u32(&bar_b[ns]));
+            bulk_g2s(sB_u + ns * B_IMG, wtile + static_cast<long long>(cb + c + TC_B_STAGES - 1) * B_IMG, B_IMG,
+                     smem_u32(&bar_b[ns]));
           }
           __syncwarp();
         }
@@ -802,17 +878,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         mbar_wait(smem_u32(&bar_asplit[ts]), (round / TC_T_STAGES) & 1, 0x40000u + round);   // split A of this chunk is in TMEM
         if (ih == 0) TC_TRACE(2, 2, c);
         tc_fence_after();
-        const uint64_t b0 = umma_desc_sw128(sB_u + bs * 2 * TC_B_TILE);
+        const uint64_t b0 = umma_desc_sw128(sB_u + bs * B_IMG);
         const uint32_t ah = tmem_u + Cfg::A_COL0 + ts * 128u + static_cast<uint32_t>(ih * 64);
         if (elect_one()) {
+          if (F16) {
+            // rows of the weight tile: [h1: 64 B | h2: 64 B]; a k-step is 16 channels = 32 B; A: h1 columns 0..15, h2 16..31
 #pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
-            const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
-            const uint32_t a = ah + static_cast<uint32_t>(8 * ks);
-            umma_tf32_ts(dh, a + 32u, bh, kIdesc, 1u);     // lo*hi
-            umma_tf32_ts(dh, a, bl, kIdesc, 1u);           // hi*lo
-            umma_tf32_ts(dh, a, bh, kIdesc, 1u);           // hi*hi
+            for (int ks = 0; ks < TC_BK / 16; ++ks) {
+              const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
+              const uint64_t bl = bh + 4u;
+              const uint32_t a = ah + static_cast<uint32_t>(8 * ks);
+              umma_f16_ts(dh, a + 16u, bh, kIdesc, 1u);    // lo*hi
+              umma_f16_ts(dh, a, bl, kIdesc, 1u);          // hi*lo
+              umma_f16_ts(dh, a, bh, kIdesc, 1u);          // hi*hi
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+              const uint64_t bh = b0 + static_cast<uint64_t>(2 * ks);
+              const uint64_t bl = bh + static_cast<uint64_t>(TC_B_TILE >> 4);
+              const uint32_t a = ah + static_cast<uint32_t>(8 * ks);
+              umma_tf32_ts(dh, a + 32u, bh, kIdesc, 1u);     // lo*hi
+              umma_tf32_ts(dh, a, bl, kIdesc, 1u);           // hi*lo
+              umma_tf32_ts(dh, a, bh, kIdesc, 1u);           // hi*hi
+            }
           }
           umma_commit(smem_u32(&bar_mma[ts]));             // TMEM A stage reusable
           umma_commit(smem_u32(&bar_bfree[bs]));           // weight stage reusable
@@ -851,26 +940,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         }
       } else if (m < rows) {
         float* yr = d.y + static_cast<long long>(m) * d.ldy;
-        const bool vec_ok = (d.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15) == 0);
+        // The epilogue is instruction bound (64 outputs per thread at N = 128): the activation is picked once per tile, not
+        // per element (act is a kernel argument), quads that lie inside cout take vector bias loads and no per-element
+        // bounds; only a quad that straddles cout goes element by element.
+        const float ap = d.act_param;
+        auto store_all = [&](auto actf) {
 #pragma unroll
-        for (int j = 0; j < ACC; j += 4) {
-          const int co = n0 + my_ch * ACC + j;
-          if (co < d.cout) {
-            float4 o;
-            o.x = activate(acc[j] + (d.bias ? __ldg(d.bias + min(co, d.cout - 1)) : 0.f), d.act, d.act_param);
-            o.y = activate(acc[j + 1] + (d.bias ? __ldg(d.bias + min(co + 1, d.cout - 1)) : 0.f), d.act, d.act_param);
-            o.z = activate(acc[j + 2] + (d.bias ? __ldg(d.bias + min(co + 2, d.cout - 1)) : 0.f), d.act, d.act_param);
-            o.w = activate(acc[j + 3] + (d.bias ? __ldg(d.bias + min(co + 3, d.cout - 1)) : 0.f), d.act, d.act_param);
-            if (vec_ok && co + 3 < d.cout) {
+          for (int j = 0; j < ACC; j += 4) {
+            const int co = n0 + my_ch * ACC + j;
+            if (al_ok && co + 3 < d.cout) {
+              const float4 bq = d.bias ? __ldg(reinterpret_cast<const float4*>(d.bias + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float4 o;
+              if (F16) {                               // out_scale is a power of two: the product is exact
+                o.x = fmaf(acc[j], out_scale, bq.x); o.y = fmaf(acc[j + 1], out_scale, bq.y);
+                o.z = fmaf(acc[j + 2], out_scale, bq.z); o.w = fmaf(acc[j + 3], out_scale, bq.w);
+              } else {
+                o.x = acc[j] + bq.x; o.y = acc[j + 1] + bq.y; o.z = acc[j + 2] + bq.z; o.w = acc[j + 3] + bq.w;
+              }
+              o.x = actf(o.x); o.y = actf(o.y); o.z = actf(o.z); o.w = actf(o.w);
+              out_max = fmaxf(fmaxf(out_max, fabsf(o.x)), fmaxf(fabsf(o.y), fmaxf(fabsf(o.z), fabsf(o.w))));
               *reinterpret_cast<float4*>(yr + co) = o;
-            } else {
-              yr[co] = o.x;
-              if (co + 1 < d.cout) yr[co + 1] = o.y;
-              if (co + 2 < d.cout) yr[co + 2] = o.z;
-              if (co + 3 < d.cout) yr[co + 3] = o.w;
+            } else if (co < d.cout) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (co + e < d.cout) {
+                  const float a = F16 ? __fmul_rn(acc[j + e], out_scale) : acc[j + e];
+                  const float o = actf(a + (d.bias ? __ldg(d.bias + co + e) : 0.f));
+                  out_max = fmaxf(out_max, fabsf(o));
+                  yr[co + e] = o;
+                }
+              }
             }
           }
-        }
+        };
+        if (d.act == WMD_ACT_ELU) store_all([](float v) { return v > 0.f ? v : expm1_nonpos(v); });
+        else if (d.act == WMD_ACT_LRELU) store_all([ap](float v) { return v > 0.f ? v : v * ap; });
+        else if (d.act == WMD_ACT_NONE) store_all([](float v) { return v; });
+        else store_all([&](float v) { return activate(v, d.act, ap); });
       }
     }
     // ---- balanced mode, stream-K fix-up: the LAST segment of a cut tile to arrive (arrival counter per tile, left at zero
@@ -894,33 +1000,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         __threadfence();
         const float* pb = partial + kBalCounterBytes / 4 + (rem_t * plan.slabs * TC_BM + my_row) * BN + my_ch * ACC;
         float* yr = d.y + static_cast<long long>(m) * d.ldy;
+        // tf32 form: bias first, then the slabs (the order of every earlier version); f16 form: slabs, scale, bias.
+        // Eight quads at a time: their slab loads are independent (L2 latency is paid once per group, not per quad)
+        constexpr int kGroup = ACC < 32 ? ACC : 32;
+#pragma unroll 1
+        for (int j0 = 0; j0 < ACC; j0 += kGroup) {
+          float4 v[kGroup / 4], bq[kGroup / 4];
 #pragma unroll
-        for (int j = 0; j < ACC; j += 4) {
-          const int co = n0 + my_ch * ACC + j;
-          if (co < d.cout) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (d.bias) {
-              v.x = __ldg(d.bias + co);
-              if (co + 1 < d.cout) v.y = __ldg(d.bias + co + 1);
-              if (co + 2 < d.cout) v.z = __ldg(d.bias + co + 2);
-              if (co + 3 < d.cout) v.w = __ldg(d.bias + co + 3);
+          for (int q = 0; q < kGroup / 4; ++q) {
+            const int co = n0 + my_ch * ACC + j0 + 4 * q;
+            bq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d.bias && co < d.cout) {
+              if (al_ok && co + 3 < d.cout) {
+                bq[q] = __ldg(reinterpret_cast<const float4*>(d.bias + co));
+              } else {
+                bq[q].x = __ldg(d.bias + co);
+                if (co + 1 < d.cout) bq[q].y = __ldg(d.bias + co + 1);
+                if (co + 2 < d.cout) bq[q].z = __ldg(d.bias + co + 2);
+                if (co + 3 < d.cout) bq[q].w = __ldg(d.bias + co + 3);
+              }
             }
-            for (int sidx = 0; sidx < nseg; ++sidx) {
-              const float4 p = __ldcg(reinterpret_cast<const float4*>(pb + static_cast<long long>(sidx) * TC_BM * BN + j));
-              v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+            v[q] = F16 ? make_float4(0.f, 0.f, 0.f, 0.f) : bq[q];
+          }
+          for (int sidx = 0; sidx < nseg; ++sidx) {
+            const float4* ps = reinterpret_cast<const float4*>(pb + static_cast<long long>(sidx) * TC_BM * BN + j0);
+#pragma unroll
+            for (int q = 0; q < kGroup / 4; ++q) {
+              const float4 pq = __ldcg(ps + q);
+              v[q].x += pq.x; v[q].y += pq.y; v[q].z += pq.z; v[q].w += pq.w;
             }
-            v.x = activate(v.x, d.act, d.act_param); v.y = activate(v.y, d.act, d.act_param);
-            v.z = activate(v.z, d.act, d.act_param); v.w = activate(v.w, d.act, d.act_param);
-            if (co + 3 < d.cout) {                   // balanced mode requires ldy % 4 == 0 and a 16-byte aligned y
-              *reinterpret_cast<float4*>(yr + co) = v;
-            } else {
-              yr[co] = v.x;
-              if (co + 1 < d.cout) yr[co + 1] = v.y;
-              if (co + 2 < d.cout) yr[co + 2] = v.z;
+          }
+#pragma unroll
+          for (int q = 0; q < kGroup / 4; ++q) {
+            const int co = n0 + my_ch * ACC + j0 + 4 * q;
+            if (co < d.cout) {
+              float4 o = v[q];
+              if (F16) {
+                o.x = __fadd_rn(__fmul_rn(o.x, out_scale), bq[q].x); o.y = __fadd_rn(__fmul_rn(o.y, out_scale), bq[q].y);
+                o.z = __fadd_rn(__fmul_rn(o.z, out_scale), bq[q].z); o.w = __fadd_rn(__fmul_rn(o.w, out_scale), bq[q].w);
+              }
+              o.x = activate(o.x, d.act, d.act_param); o.y = activate(o.y, d.act, d.act_param);
+              o.z = activate(o.z, d.act, d.act_param); o.w = activate(o.w, d.act, d.act_param);
+              out_max = fmaxf(out_max, fabsf(o.x));
+              if (co + 1 < d.cout) out_max = fmaxf(out_max, fabsf(o.y));
+              if (co + 2 < d.cout) out_max = fmaxf(out_max, fabsf(o.z));
+              if (co + 3 < d.cout) out_max = fmaxf(out_max, fabsf(o.w));
+              if (co + 3 < d.cout) {                   // balanced mode requires ldy % 4 == 0 and a 16-byte aligned y
+                *reinterpret_cast<float4*>(yr + co) = o;
+              } else {
+                yr[co] = o.x;
+                if (co + 1 < d.cout) yr[co + 1] = o.y;
+                if (co + 2 < d.cout) yr[co + 2] = o.z;
+              }
             }
           }
         }
       }
+    }
+    if (d.amax_out) {                              // max |y| of the layer for its consumers' operand scaling (order independent)
+      for (int o = 16; o > 0; o >>= 1) out_max = fmaxf(out_max, __shfl_xor_sync(0xffffffffu, out_max, o));
+      if (lane == 0 && out_max > 0.f) atomicMax(reinterpret_cast<unsigned*>(d.amax_out), __float_as_uint(out_max));
     }
     TC_TILE_TRACE(6);
     tc_fence_before();
@@ -1033,6 +1172,75 @@ __global__ void tc_reduce_kernel(const float* __restrict__ partial, int splits, 
   }
 }
 
+// ---- fp16 weight images (precision = WMD_PREC_F16X3) -----------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ x, long long count, float* __restrict__ out) {
+  float m = 0.f;
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += step) m = fmaxf(m, fabsf(__ldg(x + i)));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned*>(out), __float_as_uint(m));
+}
+
+// header word 0 holds max |w| when this runs; it is replaced by 1 / s_w by the last block... no: by a second tiny kernel
+// (finish_header) so that every pack thread reads the same maximum.
+__global__ void pack_weight_tc16_kernel(const float* __restrict__ w, unsigned char* __restrict__ out, int Cout, int c0, int c1,
+                                        int taps, int BN, long long total) {
+  const float wmax = *reinterpret_cast<const float*>(out);        // header word 0: max |w| (absmax_kernel)
+  int e = 0;
+  if (wmax > 0.f && wmax < INFINITY) {
+    int ex;
+    frexpf(wmax, &ex);
+    e = 14 - ex;
+  }
+  e = max(-100, min(100, e));
+  const float sw = ldexpf(1.f, e);
+  const int nch0 = (c0 + TC_BK - 1) / TC_BK, nch1 = (c1 + TC_BK - 1) / TC_BK;
+  const int per_tap = nch0 + nch1;
+  const int nchunks = taps * per_tap;
+  const int Cin = c0 + c1;
+  __half* img = reinterpret_cast<__half*>(out + 128);
+  const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += step) {
+    // i indexes LOGICAL (nt, chunk, n, kk); the row of a tile is 64 halves: [h1: kk 0..31 | h2: kk 0..31], 128B-swizzled
+    long long t = i;
+    const int kk = static_cast<int>(t % TC_BK); t /= TC_BK;
+    const int n = static_cast<int>(t % BN); t /= BN;
+    const int c = static_cast<int>(t % nchunks);
+    const int nt = static_cast<int>(t / nchunks);
+    const int rr = c / taps;
+    const int tap = c - rr * taps;
+    const bool src1 = rr >= nch0;
+    const int ci_local = (src1 ? rr - nch0 : rr) * TC_BK + kk;
+    const int csrc = src1 ? c1 : c0;
+    const int co = nt * BN + n;
+    float v = 0.f;
+    if (ci_local < csrc && co < Cout) {
+      const int ci = (src1 ? c0 : 0) + ci_local;
+      v = __ldg(w + (static_cast<long long>(co) * Cin + ci) * taps + tap) * sw;
+    }
+    const __half h1 = __float2half_rn(v);
+    const __half h2 = __float2half_rn(v - __half2float(h1));
+    const long long tile_base = (static_cast<long long>(nt) * nchunks + c) * (static_cast<long long>(BN) * 64);
+    // halves kk (h1) and 32 + kk (h2) of row n; 16-byte pieces (8 halves) are XOR-swizzled with the row index
+    const int p1 = kk >> 3, p2 = (32 + kk) >> 3, within = kk & 7;
+    img[tile_base + static_cast<long long>(n) * 64 + ((p1 ^ (n & 7)) << 3) + within] = h1;
+    img[tile_base + static_cast<long long>(n) * 64 + ((p2 ^ (n & 7)) << 3) + within] = h2;
+  }
+}
+__global__ void finish_header_tc16_kernel(unsigned char* out) {
+  float* h = reinterpret_cast<float*>(out);
+  const float wmax = h[0];
+  int e = 0;
+  if (wmax > 0.f && wmax < INFINITY) {
+    int ex;
+    frexpf(wmax, &ex);
+    e = 14 - ex;
+  }
+  e = max(-100, min(100, e));
+  h[1] = wmax;
+  h[0] = ldexpf(1.f, -e);                          // 1 / s_w: what the conv kernel reads
+}
+
 static int tc_tile_n(int cout) { return cout >= 96 ? 128 : (cout >= 48 ? 64 : 32); }
 
 // TMA descriptor of a source: 2-D fp32 tensor [rows][C] with row pitch ld floats, box = one row x 32 channels,
@@ -1059,9 +1267,9 @@ static int make_rows_map(CUtensorMap* tm, const float* x, int C, long long rows,
 
 static int g_shared_taps = 1;      // 3x3 layers: one raw-stage fill per (chunk, dy) shared by the three dx taps (tuning / A-B knob)
 
-template <int BN, bool SH>
+template <int BN, bool SH, bool F16>
 static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStream_t stream) {
-  using Cfg = TcCfg<BN, SH>;
+  using Cfg = TcCfg<BN, SH, F16>;
   CUtensorMap tm0, tm1;
   {
     const long long px = static_cast<long long>(d.N) * d.H * d.W;
@@ -1081,7 +1289,7 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {   // outside the cache: set it on every launch
-    int rc = record(cudaFuncSetAttribute(conv_rows_tc_kernel<BN, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int rc = record(cudaFuncSetAttribute(conv_rows_tc_kernel<BN, SH, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(Cfg::SMEM)));
     if (rc != WMD_OK) return rc;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
@@ -1089,7 +1297,7 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
   const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN) * (splits > 0 ? splits : 1);
   const long long cap = sm_count();
   const int grid = splits == 0 ? static_cast<int>(cap) : static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
-  conv_rows_tc_kernel<BN, SH><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial, tm0, tm1);
+  conv_rows_tc_kernel<BN, SH, F16><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial, tm0, tm1);
   int rc = launched();
   if (rc != WMD_OK || splits <= 1) return rc;      // whole tiles, or balanced: the kernel's own fix-up finishes cut tiles
   const int nchunks = d.taps * ((d.c0 + TC_BK - 1) / TC_BK + (d.c1 + TC_BK - 1) / TC_BK);
@@ -1137,6 +1345,45 @@ extern "C" int wmd_pack_conv_weight_tc_f32(const float* w, float* packed, int Co
   return launched();
 }
 
+extern "C" size_t wmd_conv_tc16_weight_bytes(int cout, int c0, int c1, int taps) {
+  using namespace wmd;
+  const int bn = tc_tile_n(cout);
+  const int nchunks = taps * ((c0 + TC_BK - 1) / TC_BK + (c1 + TC_BK - 1) / TC_BK);
+  return 128 + static_cast<size_t>(ceil_div(cout, bn)) * nchunks * bn * 128;
+}
+
+extern "C" int wmd_pack_conv_weight_tc16_f32(const float* w, void* packed, int Cout, int c0, int c1, int taps,
+                                             wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(w && packed, WMD_ERR_ARG);
+  WMD_REQUIRE(Cout > 0 && c0 > 0 && c1 >= 0 && (taps == 1 || taps == 9), WMD_ERR_SHAPE);
+  WMD_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, WMD_ERR_SHAPE);
+  cudaStream_t st = as_stream(stream);
+  unsigned char* out = static_cast<unsigned char*>(packed);
+  int rc = record(cudaMemsetAsync(out, 0, 128, st));
+  if (rc != WMD_OK) return rc;
+  const long long nw = static_cast<long long>(Cout) * (c0 + c1) * taps;
+  absmax_kernel<<<stride_grid(nw, 256), 256, 0, st>>>(w, nw, reinterpret_cast<float*>(out));
+  rc = launched();
+  if (rc != WMD_OK) return rc;
+  const int bn = tc_tile_n(Cout);
+  const int nchunks = taps * ((c0 + TC_BK - 1) / TC_BK + (c1 + TC_BK - 1) / TC_BK);
+  const long long total = static_cast<long long>(ceil_div(Cout, bn)) * nchunks * bn * TC_BK;
+  pack_weight_tc16_kernel<<<stride_grid(total, 256), 256, 0, st>>>(w, out, Cout, c0, c1, taps, bn, total);
+  rc = launched();
+  if (rc != WMD_OK) return rc;
+  finish_header_tc16_kernel<<<1, 1, 0, st>>>(out);
+  return launched();
+}
+
+extern "C" int wmd_amax_f32(const float* x, long long count, float* amax, wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(x && amax, WMD_ERR_ARG);
+  if (count <= 0) return WMD_OK;
+  absmax_kernel<<<stride_grid(count, 256, 16), 256, 0, as_stream(stream)>>>(x, count, amax);
+  return launched();
+}
+
 extern "C" size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits) {
   if (splits == 1) return 0;
   if (splits == 0)   // balanced: [stream-K tile][slab][256 rows][N <= 128] floats, tiles x slabs <= CTAs x kBalSlabs whatever the layer size
@@ -1160,6 +1407,7 @@ extern "C" int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* dp, int splits, 
   WMD_REQUIRE(d.taps == 1 || d.taps == 9, WMD_ERR_ARG);
   WMD_REQUIRE(d.pad_mode >= WMD_PAD_ZERO && d.pad_mode <= WMD_PAD_REPLICATE, WMD_ERR_ARG);
   WMD_REQUIRE(d.act >= WMD_ACT_NONE && d.act <= WMD_ACT_SIGMOID, WMD_ERR_ARG);
+  WMD_REQUIRE(d.precision == WMD_PREC_TF32X3 || d.precision == WMD_PREC_F16X3, WMD_ERR_ARG);
   WMD_REQUIRE(d.shift0 == 0 || d.shift0 == 1, WMD_ERR_ARG);
   WMD_REQUIRE((d.pixels == nullptr) == (d.count == nullptr), WMD_ERR_ARG);
   WMD_REQUIRE(d.N > 0 && d.H > 0 && d.W > 0 && d.c0 > 0 && d.cout > 0 && d.max_rows >= 0, WMD_ERR_SHAPE);
@@ -1188,9 +1436,17 @@ extern "C" int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* dp, int splits, 
   }
   float* partial = static_cast<float*>(ws);
   const bool sh = d.taps == 9 && g_shared_taps != 0;
+  const bool f16 = d.precision == WMD_PREC_F16X3;
+  if (f16) WMD_REQUIRE(d.amax0 != nullptr && (d.c1 == 0 || d.amax1 != nullptr), WMD_ERR_ARG);
+  if (f16) WMD_REQUIRE(splits <= 1, WMD_ERR_UNSUPPORTED);   // tc_reduce_kernel sums unscaled slabs: tf32 operands only
+  cudaStream_t st = as_stream(stream);
+#define WMD_TC_LAUNCH(BN_)                                                                                              \
+  return f16 ? (sh ? launch_tc<BN_, true, true>(d, splits, partial, st) : launch_tc<BN_, false, true>(d, splits, partial, st)) \
+             : (sh ? launch_tc<BN_, true, false>(d, splits, partial, st) : launch_tc<BN_, false, false>(d, splits, partial, st))
   switch (tc_tile_n(d.cout)) {
-    case 128: return sh ? launch_tc<128, true>(d, splits, partial, as_stream(stream)) : launch_tc<128, false>(d, splits, partial, as_stream(stream));
-    case 64: return sh ? launch_tc<64, true>(d, splits, partial, as_stream(stream)) : launch_tc<64, false>(d, splits, partial, as_stream(stream));
-    default: return sh ? launch_tc<32, true>(d, splits, partial, as_stream(stream)) : launch_tc<32, false>(d, splits, partial, as_stream(stream));
+    case 128: WMD_TC_LAUNCH(128);
+    case 64: WMD_TC_LAUNCH(64);
+    default: WMD_TC_LAUNCH(32);
   }
+#undef WMD_TC_LAUNCH
 }

@@ -20,7 +20,7 @@ static_assert(kTP / 32 == 4, "the gated variant ORs four group masks");
 template <bool GATED>
 __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                            const uint8_t* __restrict__ gate, int C, long long HW,
-                                                           int ld) {
+                                                           int ld, float* __restrict__ amax) {
   __shared__ float tile[kTT][kTP + 1];
   __shared__ unsigned marked[kTP / 32];
   const int n = blockIdx.z;
@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restri
   }
   const float* s = src + static_cast<long long>(n) * C * HW;
   float* d = dst + static_cast<long long>(n) * HW * ld;
+  float vmax = 0.f;
 #pragma unroll
   for (int r = warp; r < kTT; r += 8) {
     const int c = c0 + r;
@@ -47,8 +48,14 @@ __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restri
     for (int j = 0; j < kTP / 32; ++j) {          // four fully coalesced 128-byte requests per channel row
       if (GATED && marked[j] == 0u) continue;
       const long long p = p0 + lane + 32 * j;
-      tile[r][lane + 32 * j] = (c < C && p < HW) ? __ldg(row + p) : 0.f;
+      const float v = (c < C && p < HW) ? __ldg(row + p) : 0.f;
+      tile[r][lane + 32 * j] = v;
+      vmax = fmaxf(vmax, fabsf(v));
     }
+  }
+  if (amax) {                                    // max |x| of the map, for the consumers' fp16 operand scaling
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(vmax));
   }
   __syncthreads();
   const int q = lane & 7;                        // channel quad of this lane
@@ -144,9 +151,10 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 __global__ void __launch_bounds__(256) gather_rows_list_kernel(const float* __restrict__ src, float* __restrict__ rows,
                                                                int ld, int C, const int32_t* __restrict__ pixels,
                                                                const int32_t* __restrict__ count, int max_rows,
-                                                               unsigned HW) {
+                                                               unsigned HW, float* __restrict__ amax) {
   __shared__ float tile[kTT][kTP + 1];
-  __shared__ long long base[kTP];                              // (n*C)*HW + yx of the tile's pixels, -1 past the list
+  __shared__ long long base[kTP];
+  float vmax = 0.f;                              // (n*C)*HW + yx of the tile's pixels, -1 past the list
   const int M = count ? min(*count, max_rows) : max_rows;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ctiles = (ld + kTT - 1) / kTT;
@@ -172,7 +180,9 @@ __global__ void __launch_bounds__(256) gather_rows_list_kernel(const float* __re
 #pragma unroll
       for (int j = 0; j < kTP / 32; ++j) {
         const long long b = base[lane + 32 * j];
-        tile[r][lane + 32 * j] = (c < C && b >= 0) ? __ldg(src + b + coff) : 0.f;
+        const float v = (c < C && b >= 0) ? __ldg(src + b + coff) : 0.f;
+        tile[r][lane + 32 * j] = v;
+        vmax = fmaxf(vmax, fabsf(v));
       }
     }
     __syncthreads();
@@ -187,6 +197,10 @@ __global__ void __launch_bounds__(256) gather_rows_list_kernel(const float* __re
             make_float4(tile[4 * q][pl], tile[4 * q + 1][pl], tile[4 * q + 2][pl], tile[4 * q + 3][pl]);
     }
     __syncthreads();
+  }
+  if (amax) {                                    // max |x| of the gathered rows, for the consumer's fp16 operand scaling
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(vmax));
   }
 }
 
@@ -249,7 +263,7 @@ extern "C" int wmd_nchw_to_rows_f32(const float* src, float* dst, int N, int C, 
   if (N == 0) return WMD_OK;
   dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
   WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
-  nchw_to_rows_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, dst, nullptr, C, HW, ld);
+  nchw_to_rows_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, dst, nullptr, C, HW, ld, nullptr);
   return launched();
 }
 
@@ -261,7 +275,7 @@ extern "C" int wmd_nchw_to_rows_gated_f32(const float* src, float* dst, const ui
   if (N == 0) return WMD_OK;
   dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
   WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
-  nchw_to_rows_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, dst, gate, C, HW, ld);
+  nchw_to_rows_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, dst, gate, C, HW, ld, nullptr);
   return launched();
 }
 
@@ -301,7 +315,35 @@ extern "C" int wmd_gather_rows_list_f32(const float* src_nchw, float* rows, int 
   if (max_rows == 0 || N == 0) return WMD_OK;
   const long long tiles = static_cast<long long>(ceil_div(max_rows, kTP)) * ceil_div(ld, kTT);
   gather_rows_list_kernel<<<stride_grid(tiles * 256, 256, 6), 256, 0, as_stream(stream)>>>(
-      src_nchw, rows, ld, C, pixels, count, max_rows, static_cast<unsigned>(static_cast<long long>(H) * W));
+      src_nchw, rows, ld, C, pixels, count, max_rows, static_cast<unsigned>(static_cast<long long>(H) * W), nullptr);
+  return launched();
+}
+
+extern "C" int wmd_gather_rows_list_amax_f32(const float* src_nchw, float* rows, int ld, int C, const int32_t* pixels,
+                                             const int32_t* count, int max_rows, int N, int H, int W, float* amax,
+                                             wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(src_nchw && rows, WMD_ERR_ARG);
+  WMD_REQUIRE((pixels == nullptr) == (count == nullptr), WMD_ERR_ARG);
+  WMD_REQUIRE(C > 0 && ld >= C && ld % 4 == 0 && N >= 0 && H > 0 && W > 0 && max_rows >= 0, WMD_ERR_SHAPE);
+  WMD_REQUIRE((reinterpret_cast<uintptr_t>(rows) & 15) == 0, WMD_ERR_SHAPE);
+  WMD_REQUIRE(static_cast<long long>(N) * H * W < (1ll << 31), WMD_ERR_SHAPE);
+  if (max_rows == 0 || N == 0) return WMD_OK;
+  const long long tiles = static_cast<long long>(ceil_div(max_rows, kTP)) * ceil_div(ld, kTT);
+  gather_rows_list_kernel<<<stride_grid(tiles * 256, 256, 6), 256, 0, as_stream(stream)>>>(
+      src_nchw, rows, ld, C, pixels, count, max_rows, static_cast<unsigned>(static_cast<long long>(H) * W), amax);
+  return launched();
+}
+
+extern "C" int wmd_nchw_to_rows_amax_f32(const float* src, float* dst, int N, int C, long long HW, int ld, float* amax,
+                                         wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(src && dst, WMD_ERR_ARG);
+  WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
+  if (N == 0) return WMD_OK;
+  dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
+  WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
+  nchw_to_rows_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, dst, nullptr, C, HW, ld, amax);
   return launched();
 }
 

@@ -296,7 +296,13 @@ class _WaveDecoderBase(nn.Module):
         dev = feats[-1].device
         if n == 0:
             return self._empty_outputs(feats, sparse_levels, with_masks)
-        x_rows, x_c, prev_map = ops.nchw_to_rows(feats[4]), feats[4].shape[1], None
+        # max |x| of every tensor a tensor-core conv reads (device scalars, zeroed here, raised by the producers): the
+        # fp16-pair operand form scales by a power of two chosen from them (ops.default_conv_precision)
+        track = ops.default_conv_precision() == "f16x3"
+        amax = torch.zeros(24, dtype=torch.float32, device=dev) if track else None
+        slot = (lambda k: amax[k:k + 1]) if track else (lambda k: None)
+        x_rows, x_c, prev_map = ops.nchw_to_rows(feats[4], amax=slot(0)), feats[4].shape[1], None
+        x_amax = slot(0)
         # layout moves of the skip maps (NCHW -> pixel-major rows), two options on top of the plain in-order transpose:
         #  gated_layout   a sparse level reads its skip map only under the upsample mask S3 (sparse_upsample:
         #                 skip[mask], layers.py:500), so only those rows are produced - the move scales with density;
@@ -330,14 +336,17 @@ class _WaveDecoderBase(nn.Module):
                 s3 = _side_stream(dev, 3) if self.overlap_compaction else None
                 if s3 is not None:
                     (map3, pix3, off3), _ = ops.compact(masks["S3"], stream=s3, ws_slot=3)
-                    skip_rows, skip_done = ops.gather_rows_list(skip, pix3, off3[n:], stream=s3)
+                    skip_rows, skip_done = ops.gather_rows_list(skip, pix3, off3[n:], stream=s3, amax=slot(i))
                 else:
                     map3, pix3, off3 = ops.compact(masks["S3"], ws_slot=3)
-                    skip_rows = ops.gather_rows_list(skip, pix3, off3[n:])
-            elif side is not None:
-                skip_rows, skip_done = ops.nchw_to_rows(skip, stream=side, gate=skip_gate)
+                    skip_rows = ops.gather_rows_list(skip, pix3, off3[n:], amax=slot(i))
+                skip_amax = slot(i)
             else:
-                skip_rows = ops.nchw_to_rows(skip, gate=skip_gate)
+                skip_amax = slot(i) if skip_gate is None else None      # the gated move leaves rows unwritten: no maximum
+                if side is not None:
+                    skip_rows, skip_done = ops.nchw_to_rows(skip, stream=side, gate=skip_gate, amax=skip_amax)
+                else:
+                    skip_rows = ops.nchw_to_rows(skip, gate=skip_gate, amax=skip_amax)
             if with_masks:
                 for name, key in (("lowres_mask", "S1"), ("upconv0_mask", "S2"), ("upsample_mask", "S3"),
                                   ("upconv1_mask", "S4"), ("wavelet_mask", "S5")):
@@ -364,7 +373,8 @@ class _WaveDecoderBase(nn.Module):
                     _, pix5, off5 = ops.compact(masks["S5"], want_idxmap=False, want_pixels=not self.fused_tail)
                 counts[i] = (off2, off4, off5)
                 xa = ops.conv_rows(x_rows, x_c, wp0, b0, c, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, map0=gmap,
-                                   pixels=pix2, count=off2[n:], m_in0=_pm(lambda: (gmap >= 0).sum()))
+                                   pixels=pix2, count=off2[n:], m_in0=_pm(lambda: (gmap >= 0).sum()),
+                                   amax0=x_amax, amax_out=slot(4 + i))
                 if skip_done is not None:
                     torch.cuda.current_stream(dev).wait_event(skip_done)
                 if ev4 is not None:
@@ -372,20 +382,23 @@ class _WaveDecoderBase(nn.Module):
                     torch.cuda.current_stream(dev).wait_event(ev5)
                 xb = ops.conv_rows(xa, c, wp1, b1, c, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_ELU, map0=map2,
                                    shift0=1, x1=skip_rows, c1=cs, map1=map3, gate=masks["S3"], pixels=pix4, count=off4[n:],
-                                   m_in0=off2[n:], m_in1=_pm(lambda: masks["S3"].sum()))
+                                   m_in0=off2[n:], m_in1=_pm(lambda: masks["S3"].sum()),
+                                   amax0=slot(4 + i), amax1=skip_amax, amax_out=slot(8 + i))
                 if mlp is None:
                     t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1,
-                                      pixels=pix4, count=off4[n:], m_in0=off4[n:])
+                                      pixels=pix4, count=off4[n:], m_in0=off4[n:], amax0=slot(8 + i), amax_out=slot(12 + i))
                 head_kw = dict(idxmap=map4, pixels=pix5, count=off5[n:])
                 prev_map = map4
             else:
-                xa = ops.conv_rows(x_rows, x_c, wp0, b0, c, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, map0=prev_map)
+                xa = ops.conv_rows(x_rows, x_c, wp0, b0, c, n, h, w, pad=PAD_REFLECT, act=ACT_ELU, map0=prev_map,
+                                   amax0=x_amax, amax_out=slot(4 + i))
                 if skip_done is not None:
                     torch.cuda.current_stream(dev).wait_event(skip_done)
                 xb = ops.conv_rows(xa, c, wp1, b1, c, n, 2 * h, 2 * w, pad=PAD_REFLECT, act=ACT_ELU, shift0=1,
-                                   x1=skip_rows, c1=cs)
+                                   x1=skip_rows, c1=cs, amax0=slot(4 + i), amax1=skip_amax, amax_out=slot(8 + i))
                 if mlp is None:
-                    t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1)
+                    t = ops.conv_rows(xb, c, w1x1, b1x1, c1x1, n, 2 * h, 2 * w, taps=1, act=ACT_LRELU, act_param=0.1,
+                                      amax0=slot(8 + i), amax_out=slot(12 + i))
                 head_kw = {}
                 if with_masks and i != 4:
                     # dense level under a thresholded mask: yh * wavelet_mask (depth_decoder.py:271-272)
@@ -402,9 +415,10 @@ class _WaveDecoderBase(nn.Module):
             if mlp is not None:
                 z = ops.head_mlp(xb, c, mlp, c1x1, 0.1, count=off4[n:] if sparse else None, max_rows=n * 4 * h * w)
             elif sparse:
-                z = ops.conv_rows(t, c1x1, wz, None, 54, n, 2 * h, 2 * w, taps=1, pixels=pix4, count=off4[n:], m_in0=off4[n:])
+                z = ops.conv_rows(t, c1x1, wz, None, 54, n, 2 * h, 2 * w, taps=1, pixels=pix4, count=off4[n:], m_in0=off4[n:],
+                                  amax0=slot(12 + i))
             else:
-                z = ops.conv_rows(t, c1x1, wz, None, 63 if ll_in_gemm else 54, n, 2 * h, 2 * w, taps=1)
+                z = ops.conv_rows(t, c1x1, wz, None, 63 if ll_in_gemm else 54, n, 2 * h, 2 * w, taps=1, amax0=slot(12 + i))
             if ll_in_gemm:
                 yl = ops.head_gather(z, 1, self.convs[("waveconv", i, 0)][2].conv.bias.detach(), n, 2 * h, 2 * w, 1,
                                      scale=float(2 ** i), act=ACT_SIGMOID, pad=PAD_REFLECT, col0=54)
@@ -433,7 +447,7 @@ class _WaveDecoderBase(nn.Module):
                                                                disp_scale=1.0 / 2 ** (i - 1), clamp01=True)
             yl = yl_next
             out[("disp", i - 1)] = disp
-            x_rows, x_c = xb, c
+            x_rows, x_c, x_amax = xb, c, slot(8 + i)
             h, w = 2 * h, 2 * w
         stacked = torch.stack([torch.stack(counts[i]) for i in sorted(counts, reverse=True)]) if counts else None
         return out, stacked

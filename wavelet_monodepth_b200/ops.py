@@ -343,7 +343,18 @@ def rows_view(x):
 
 
 @_on_device
-def nchw_to_rows(x, ld=None, stream=None, gate=None):
+def amax_rows(x, out):
+    """out (1-element device tensor, pre-zeroed or holding a lower bound) = max(out, max |x|): for sources no libwmd kernel
+    produced (channels_last maps used in place)."""
+    lib = _lib.load()
+    with _prof('amax', lambda: dict(count=x.numel())):
+        rc = lib.wmd_amax_f32(_lib.ptr(x, _f32), x.numel(), _lib.ptr(out, _f32), _lib.stream_ptr())
+    _lib.check(rc, "wmd_amax_f32")
+    return out
+
+
+@_on_device
+def nchw_to_rows(x, ld=None, stream=None, gate=None, amax=None):
     """(N,C,H,W) -> rows (N*H*W, ld) pixel-major.  Zero-copy when x is channels_last and C % 4 == 0.
 
     gate: optional uint8 (N,1,H,W) / (N,H,W) mask of the pixels whose rows will be read later: only those rows are
@@ -367,6 +378,8 @@ def nchw_to_rows(x, ld=None, stream=None, gate=None):
         dev = x.device
         if x.dtype == _f32 and ld == c and x.permute(0, 2, 3, 1).is_contiguous() and x.data_ptr() % 16 == 0:
             rows = x.permute(0, 2, 3, 1).reshape(n * h * w, c)
+            if amax is not None:
+                amax_rows(rows, amax)
             return (rows, None) if stream is not None else rows
         x = _dense(x)
     if gate is not None:
@@ -378,7 +391,9 @@ def nchw_to_rows(x, ld=None, stream=None, gate=None):
     def launch():
         marked = _pm_count(gate)
         with _prof('nchw_to_rows', lambda: dict(n=n, c=c, hw=h * w, ld=ld, marked=marked, host=on_host)):
-            if gate is None:
+            if gate is None and amax is not None:
+                rc = lib.wmd_nchw_to_rows_amax_f32(_lib.ptr(x), _lib.ptr(rows), n, c, h * w, ld, _lib.ptr(amax, _f32), _lib.stream_ptr())
+            elif gate is None:
                 rc = lib.wmd_nchw_to_rows_f32(_lib.ptr(x), _lib.ptr(rows), n, c, h * w, ld, _lib.stream_ptr())
             else:
                 rc = lib.wmd_nchw_to_rows_gated_f32(_lib.host_ptr(x, _f32), _lib.ptr(rows), _lib.ptr(gate), n, c, h * w, ld,
@@ -430,7 +445,7 @@ def gather_rows(x_nchw, pixels, count, max_rows=None, ld=None):
 
 
 @_on_device
-def gather_rows_list(x, pixels, count, ld=None, stream=None):
+def gather_rows_list(x, pixels, count, ld=None, stream=None, amax=None):
     """Compact rows of the listed pixels of an NCHW map: rows[m] = x[n, :, y, x] for pixels[m] (wmd_gather_rows_list_f32).
 
     x: (N,C,H,W) CUDA tensor or PINNED HOST tensor (read in place over PCIe: only the listed pixels cross the bus).
@@ -450,8 +465,9 @@ def gather_rows_list(x, pixels, count, ld=None, stream=None):
 
     def launch():
         with _prof('gather_rows_list', lambda: dict(c=c, ld=ld, count=count, max_rows=n * h * w, host=on_host)):
-            rc = lib.wmd_gather_rows_list_f32(_lib.host_ptr(x, _f32), _lib.ptr(rows), ld, c, _lib.ptr(pixels, _i32),
-                                              _lib.ptr(count, _i32), n * h * w, n, h, w, _lib.stream_ptr())
+            rc = lib.wmd_gather_rows_list_amax_f32(_lib.host_ptr(x, _f32), _lib.ptr(rows), ld, c, _lib.ptr(pixels, _i32),
+                                                   _lib.ptr(count, _i32), n * h * w, n, h, w, _lib.ptr(amax, _f32),
+                                                   _lib.stream_ptr())
         _lib.check(rc, "wmd_gather_rows_list_f32")
 
     if stream is None:
@@ -498,14 +514,27 @@ TC_BALANCE_MIN_CHUNKS = int(__import__("os").environ.get("WMD_TC_BALANCE_MIN_CHU
 
 class PackedW:
     """A conv weight packed for one of the two gather-GEMM engines ('simt' fp32 FMA, 'tc' tcgen05 3xTF32)."""
-    __slots__ = ("data", "kind", "taps", "c0", "c1", "cout")
+    __slots__ = ("data", "kind", "taps", "c0", "c1", "cout", "data16")
 
-    def __init__(self, data, kind, taps, c0, c1, cout):
+    def __init__(self, data, kind, taps, c0, c1, cout, data16=None):
         self.data, self.kind, self.taps, self.c0, self.c1, self.cout = data, kind, taps, c0, c1, cout
+        self.data16 = data16          # 'tc' only: fp16-pair image for precision f16x3 (wmd_pack_conv_weight_tc16_f32)
 
 
 TC_MIN_K = 128        # shallower reductions (1x1 heads of the fine levels) do not amortise the tile prologue
 TC_MIN_COUT = 32      # tcgen05 tiles are 256 x {128, 64, 32}; below that the FMA tiles / head kernel take over
+
+
+def default_conv_precision():
+    """Operand form of the tcgen05 engine: env WMD_CONV_PRECISION = tf32x3 (default) | f16x3.
+
+    Both are fp32-faithful error-compensated splits with fp32 accumulation (22 mantissa bits per operand, three MMAs per
+    product).  f16x3 feeds fp16 pairs of power-of-two scaled operands - half the MMA instructions - and needs the max |x|
+    of each source (tracked on the device by the producers, see conv_rows amax*); launches that lack it use tf32x3.
+    Opt-in: on B200 the conversion work of the split warps, not the tensor pipe, bounds the kernel in that form, so it is
+    only ~4 % faster per layer while the max tracking costs more than that elsewhere."""
+    import os
+    return os.environ.get("WMD_CONV_PRECISION", "tf32x3")
 
 
 def default_conv_kind():
@@ -518,8 +547,9 @@ def default_conv_kind():
 
 
 @_on_device
-def pack_weight(weight, c1=0, kind=None):
+def pack_weight(weight, c1=0, kind=None, precision=None):
     """(Cout,Cin,k,k) conv weight -> PackedW.  c1 = trailing input channels that come from gather source 1.
+    precision ('tc' only): 'f16x3' also builds the fp16-pair image (default: default_conv_precision()).
 
     simt: [k*k][Cin][ldw] rows (ldw = pad4(Cout)).  tc: per (n-tile, 32-channel chunk) swizzled smem images
     [tf32 hi | tf32 lo] (chunk boundaries follow the two gather sources, hence c1 matters)."""
@@ -536,7 +566,12 @@ def pack_weight(weight, c1=0, kind=None):
         packed = torch.empty((nfl,), dtype=_f32, device=wt.device)
         rc = lib.wmd_pack_conv_weight_tc_f32(_lib.ptr(wt), _lib.ptr(packed), cout, c0, c1, taps, _lib.stream_ptr())
         _lib.check(rc, "wmd_pack_conv_weight_tc_f32")
-        return PackedW(packed, "tc", taps, c0, c1, cout)
+        packed16 = None
+        if (precision or default_conv_precision()) == "f16x3":
+            packed16 = torch.empty((lib.wmd_conv_tc16_weight_bytes(cout, c0, c1, taps),), dtype=_u8, device=wt.device)
+            rc = lib.wmd_pack_conv_weight_tc16_f32(_lib.ptr(wt), _lib.ptr(packed16), cout, c0, c1, taps, _lib.stream_ptr())
+            _lib.check(rc, "wmd_pack_conv_weight_tc16_f32")
+        return PackedW(packed, "tc", taps, c0, c1, cout, packed16)
     ldw = pad4(cout)
     packed = torch.empty((taps * cin, ldw), dtype=_f32, device=wt.device)
     rc = lib.wmd_pack_conv_weight_f32(_lib.ptr(wt), _lib.ptr(packed), cout, cin, taps, ldw, _lib.stream_ptr())
@@ -548,7 +583,7 @@ def pack_weight(weight, c1=0, kind=None):
 @_on_device
 def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act=ACT_NONE, act_param=0.0,
               map0=None, shift0=0, x1=None, c1=0, gate=None, pixels=None, count=None, max_rows=None, out=None,
-              m_in0=None, m_in1=None, splits=None, map1=None):
+              m_in0=None, m_in1=None, splits=None, map1=None, amax0=None, amax1=None, amax_out=None):
     """Gather-GEMM convolution on pixel-major rows; see wmd_conv_rows_f32 in include/wmd.h.
 
     m_in0 / m_in1: optional active-row counts of the two sources (ints or 1-element device tensors), used only
@@ -579,10 +614,21 @@ def conv_rows(x0, c0, wpacked, bias, cout, n, h, w, taps=9, pad=PAD_REFLECT, act
     d.y, d.ldy = _lib.ptr(out, _f32), out.shape[1]
     d.act, d.act_param = act, float(act_param)
     d.rows0 = int(x0.shape[0])
+    # fp16-pair operands when the weights have that image and every source's max |x| is known (1-element device tensors);
+    # amax_out (optional): device scalar raised to max |y|, for the consumers of this layer
+    # (the split-K form with an external reduction keeps the tf32 operands: its reduction kernel adds unscaled slabs)
+    if wpacked.kind == "tc" and splits is None:
+        splits = tc_splits(max_rows, cout, taps * (-(-c0 // 32) + -(-c1 // 32)), dev, out.shape[1])
+    use16 = (wpacked.kind == "tc" and wpacked.data16 is not None and amax0 is not None and
+             (x1 is None or amax1 is not None) and splits in (0, 1))
+    d.precision = _lib.PREC_F16X3 if use16 else _lib.PREC_TF32X3
+    d.amax0, d.amax1 = (_lib.ptr(amax0, _f32), _lib.ptr(amax1, _f32) if x1 is not None else None) if use16 else (None, None)
+    d.amax_out = _lib.ptr(amax_out, _f32)
+    if use16:
+        d.w = _lib.ptr(wpacked.data16, _u8)
     info = lambda: dict(n=n, h=h, w=w, taps=taps, c0=c0, c1=c1, cout=cout, shift0=shift0, count=count,   # noqa: E731
-                        max_rows=max_rows, m_in0=m_in0, m_in1=m_in1, kind=wpacked.kind)
+                        max_rows=max_rows, m_in0=m_in0, m_in1=m_in1, kind=wpacked.kind, f16=use16)
     if wpacked.kind == "tc":
-        splits = tc_splits(max_rows, cout, taps * (-(-c0 // 32) + -(-c1 // 32)), dev, out.shape[1]) if splits is None else splits
         ws = None
         if splits != 1:
             ws = _scratch.splitk(dev, lib.wmd_conv_tc_splitk_ws_bytes(max_rows, out.shape[1], splits))
