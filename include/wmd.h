@@ -218,6 +218,9 @@ int wmd_pack_conv_weight_tc16_f32(const float* w, void* packed, int Cout, int c0
  * kernel produced (channels_last feature maps used in place).  The layout moves below take an optional `amax` too. */
 int wmd_amax_f32(const float* x, long long count, float* amax, wmd_stream_t stream);
 int wmd_nchw_to_rows_amax_f32(const float* src, float* dst, int N, int C, long long HW, int ld, float* amax, wmd_stream_t stream);
+/* gated move: the maximum covers the 32-pixel groups that hold a marked pixel (a superset of the rows written) */
+int wmd_nchw_to_rows_gated_amax_f32(const float* src, float* dst, const uint8_t* gate, int N, int C, long long HW, int ld,
+                                    float* amax, wmd_stream_t stream);
 int wmd_gather_rows_list_amax_f32(const float* src_nchw, float* rows, int ld, int C, const int32_t* pixels,
                                   const int32_t* count, int max_rows, int N, int H, int W, float* amax, wmd_stream_t stream);
 size_t wmd_conv_tc_weight_floats(int cout, int c0, int c1, int taps);

@@ -2,6 +2,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+from wavelet_monodepth_b200 import _lib
+if os.environ.get('WMD_LIB_PATH'):
+    _lib.LIB_PATH = os.path.abspath(os.environ['WMD_LIB_PATH'])
 import bench
 from wavelet_monodepth_b200 import ops
 from wavelet_monodepth_b200.kitti_decoders import SparseDepthWaveProgressiveDecoder

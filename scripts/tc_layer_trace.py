@@ -50,6 +50,16 @@ def report(info):
     rows = int(info["count"][0]) if info["count"] is not None else info["rows"]
     print("launch %d: taps %d cin %d+%d cout %d rows %d, %d chunks/tile, sh=%d" %
           (info["k"], info["taps"], info["c0"], info["c1"], info["cout"], rows, nch, sh))
+    # CTA 0's clock span over the launch's event time = the SM clock this kernel actually ran at
+    last = 0
+    for i in range(1, 64):                       # entries past this launch's tiles are left over from earlier launches
+        if tt[i, 0] >= tt[last, 7] and tt[i, 7] > tt[i, 0]:
+            last = i
+        else:
+            break
+    span = tt[last, 7] - tt[0, 0]
+    print("   launch %.1f us; CTA 0 first..last trace point %d clk -> SM clock >= %.2f GHz (traced tiles only: first %d)" %
+          (state.get("us", 0.0), span, span / max(state.get("us", 1.0), 1e-9) / 1e3, 64))
     labels = ["tables", "first raw A", "chunk loop", "last epoch wait", "drain", "store", "end barrier"]
     for i in range(3):
         if tt[i, 7] <= tt[i, 0]:
@@ -75,7 +85,16 @@ def report(info):
 
 
 def hooked(x0, c0, wpacked, bias, cout, n_, h, w, **kw):
+    timed = wpacked.kind == "tc" and state["i"] in ks
+    if timed:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     y = real(x0, c0, wpacked, bias, cout, n_, h, w, **kw)
+    if timed:
+        e1.record()
+        torch.cuda.synchronize()
+        state["us"] = e0.elapsed_time(e1) * 1e3
     if wpacked.kind == "tc":
         k = state["i"]
         state["i"] += 1

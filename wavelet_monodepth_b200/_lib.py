@@ -112,6 +112,7 @@ SIGNATURES = {
     "wmd_pack_conv_weight_tc16_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "wmd_amax_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
     "wmd_nchw_to_rows_amax_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p]),
+    "wmd_nchw_to_rows_gated_amax_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p]),
     "wmd_gather_rows_list_amax_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                               c_int, c_void_p, c_void_p]),
     "wmd_conv_tc_set_shared_taps": (c_int, [c_int]),

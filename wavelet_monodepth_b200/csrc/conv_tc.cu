@@ -53,7 +53,7 @@ constexpr int TC_GATHER_WARPS = 5;              // warps 8-12
 constexpr int TC_WLOAD_WARP = 13;               // warp 13: weight (B) loader - keeps the issuers' loop free of the stage-reuse wait
 constexpr int TC_ISSUERS = 2;                   // warps 14-15: one per M half, each the only writer of its accumulator
 constexpr int TC_A_STAGES = 3;                  // raw A tiles in shared memory (two gathers in flight + one being split)
-constexpr int TC_T_STAGES_MAX = 3;              // split A stages in tensor memory: 2 (N = 128) or 3 (N <= 64), see TcCfg
+constexpr int TC_T_STAGES_MAX = 4;              // split A stages in tensor memory: 2 (N = 128) or 3 (N <= 64), 4 in the f16 form, see TcCfg
 constexpr int TC_B_STAGES_MAX = 4;              // [Bhi | Blo] images in shared memory: 3 (N = 128) or 4 (N <= 64)
 constexpr int TC_A_TILE = TC_BM * TC_BK * 4;    // 32 KB raw fp32
 constexpr int TC_TABLES = 2 * 9 * TC_BM * 4;
@@ -82,13 +82,19 @@ struct TcCfg {
   // memory are full; at N <= 64 the issue is short (12 x ~35 clk per half) and the measured period was twice it
   // (scripts/tc_layer_trace.py: 1715 clk vs 960 of issue), so those tiles take a third A stage (TMEM columns 128..511 are
   // free next to <= 128 accumulator columns) and a fourth weight stage.
-  static constexpr int T_STAGES = BN <= 64 ? 3 : 2;
-  static constexpr int B_STAGES = BN <= 64 ? 4 : 3;
-  static constexpr uint32_t A_COL0 = 512u - T_STAGES * 128u;        // first TMEM column of the split A operand
+  // f16 form: a stage is half as wide (per M half 16 columns of h1 + 16 of h2), so four fit at every N and the split
+  // warps never wait for the MMAs of an earlier chunk; its weight images are half as large: four stages as well.
+  static constexpr int A_STAGE = F16 ? 64 : 128;                    // TMEM columns of one split A stage (both M halves)
+  static constexpr int T_STAGES = F16 ? 4 : (BN <= 64 ? 3 : 2);
+  static constexpr int B_STAGES = (F16 || BN <= 64) ? 4 : 3;
+  static constexpr uint32_t A_COL0 = 512u - T_STAGES * A_STAGE;     // first TMEM column of the split A operand
   static constexpr size_t SMEM = static_cast<size_t>(A_BYTES) + static_cast<size_t>(B_STAGES) * B_IMG + TC_TABLES +
                                  (SH ? TC_SH_TABLES : 0) + 1024;
   static_assert(2 * BN <= static_cast<int>(A_COL0), "accumulators must leave the A operand's TMEM columns free");
 };
+#ifndef WMD_TC_EXP
+#define WMD_TC_EXP 0                              // timing ablations of scripts/tc_ablate.py (non-zero: results are WRONG)
+#endif
 constexpr int kFlushChunks = 32;                // epoch length: K = 1024 per TMEM accumulation run
 constexpr int32_t kNoRow = -1;                  // tap-table entry of an inactive / padded source: an out-of-bounds TMA row reads zeros
 
@@ -137,6 +143,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
     if (done) return;
   }
   MBAR_FAIL(id);
+}
+// one non-blocking look (per-lane result; the user votes when it consumes it).  Issued a few hundred clocks before the
+// answer is needed - the ~200 clk round trip of a barrier query then overlaps other work; a `false` just means the
+// blocking wait still has to run
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
@@ -673,6 +693,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       int tapi = cb % 9, rri = cb / 9;
       int gpos = cb % gsz;
       uint32_t fround = fround0;
+      uint32_t pre_raw = 0, pre_mma = 0;              // early looks at THIS chunk's barriers, taken during the previous chunk
       for (int c = 0; c < len; ++c) {
         const uint32_t round = round0 + c;
         const uint32_t ts = round % TC_T_STAGES;
@@ -684,7 +705,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         bool zero_row = false;
         if (SH) {
           const uint32_t st = fround % TC_SH_STAGES;
-          if (c == 0 || gpos == 0) mbar_wait(smem_u32(&bar_raw_full[st]), (fround / TC_SH_STAGES) & 1, 0x20000u + round);
+          if ((c == 0 || gpos == 0) && !__all_sync(0xffffffffu, pre_raw != 0u)) mbar_wait(smem_u32(&bar_raw_full[st]), (fround / TC_SH_STAGES) & 1, 0x20000u + round);
           int slot = my_row;
           if (gsz == 3 && gpos != 1) slot = slots[(((rri >= nch0 ? 3 : 0) + tapi / 3) * 2 + (gpos >> 1)) * TC_BM + my_row];
           zero_row = slot == kZeroSlot;
@@ -696,7 +717,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           if (++tapi == 9) { tapi = 0; ++rri; }
         } else {
           const uint32_t rs = round % TC_A_STAGES;
-          mbar_wait(smem_u32(&bar_raw_full[rs]), (round / TC_A_STAGES) & 1, 0x20000u + round);
+          if (!__all_sync(0xffffffffu, pre_raw != 0u)) mbar_wait(smem_u32(&bar_raw_full[rs]), (round / TC_A_STAGES) & 1, 0x20000u + round);
           rowp = sA_base + rs * TC_A_TILE + my_row * 128;
           swz = static_cast<uint32_t>(my_row & 7);
           release_bar = smem_u32(&bar_raw_empty[rs]);
@@ -716,7 +737,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           }
         }
         // TMEM A stage free?  It was read by the MMAs of round - T_STAGES.
-        if (round >= TC_T_STAGES) mbar_wait(smem_u32(&bar_mma[ts]), ((round - TC_T_STAGES) / TC_T_STAGES) & 1, 0x28000u + round);
+        if (round >= TC_T_STAGES && !__all_sync(0xffffffffu, pre_mma != 0u)) mbar_wait(smem_u32(&bar_mma[ts]), ((round - TC_T_STAGES) / TC_T_STAGES) & 1, 0x28000u + round);
         tc_fence_after();
         if (kEarly) {
           // hand the raw stage back only once the row has provably arrived in registers: one dependent use of every
@@ -729,7 +750,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           if (lane == 0 && release_bar) mbar_arrive(release_bar);       // raw stage may be overwritten
         }
         if (warp == 0) TC_TRACE(0, 2, c);
-        const uint32_t ta = tmem_acc + lane_field + Cfg::A_COL0 + ts * 128u + static_cast<uint32_t>(my_half * 64);
+        const uint32_t ta = tmem_acc + lane_field + Cfg::A_COL0 + ts * Cfg::A_STAGE + static_cast<uint32_t>(my_half * (Cfg::A_STAGE / 2));
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {              // 16 channels at a time
           uint4 v4[4];
@@ -737,6 +758,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           for (int q = 0; q < 4; ++q) {
             if (kEarly) {
               v4[q] = rawv[kEarly ? 4 * hf + q : 0];
+            } else if (WMD_TC_EXP == 2 || WMD_TC_EXP == 3) {
+              v4[q] = make_uint4(round, swz, ts, 4u * hf + q);   // ablation: no shared-memory row reads
             } else {
               v4[q] = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(4 * hf + q) ^ swz) << 4));
               if (SH && zero_row) v4[q] = make_uint4(0u, 0u, 0u, 0u);
@@ -746,6 +769,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
             // x * s (s a power of two: exact) = h1 + h2 with h1 = fp16(x s) and h2 = fp16(x s - h1): 22 mantissa bits, the
             // precision of the tf32 hi / lo pair; two halves per 32-bit TMEM column, lower channel in the lower half
             uint32_t h1[8], h2[8];
+#if WMD_TC_EXP >= 1 && WMD_TC_EXP <= 3
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {              // ablation: no conversion arithmetic
+              h1[2 * q] = v4[q].x; h1[2 * q + 1] = v4[q].y; h2[2 * q] = v4[q].z; h2[2 * q + 1] = v4[q].w;
+            }
+#else
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float b0 = __uint_as_float(v4[q].x) * ascale, b1 = __uint_as_float(v4[q].y) * ascale;
@@ -756,6 +785,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
               h2[2 * q] = pack_f16x2(b0 - f16_lo_to_f32(p0), b1 - f16_hi_to_f32(p0));
               h2[2 * q + 1] = pack_f16x2(b2 - f16_lo_to_f32(p1), b3 - f16_hi_to_f32(p1));
             }
+#endif
             tmem_st8(ta + static_cast<uint32_t>(8 * hf), h1);
             tmem_st8(ta + 16u + static_cast<uint32_t>(8 * hf), h2);
           } else {
@@ -778,7 +808,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
           if (lane == 0 && release_bar) mbar_arrive(release_bar);       // raw stage may be overwritten
         }
         if (warp == 0) TC_TRACE(0, 3, c);
-        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        // early look at the next chunk's barriers: the queries' latency overlaps the tcgen05.st drain below
+        pre_raw = pre_mma = 0;
+        if (c + 1 < len) {
+          const uint32_t nr = round + 1;
+          if (nr >= TC_T_STAGES) pre_mma = mbar_test(smem_u32(&bar_mma[nr % TC_T_STAGES]), ((nr - TC_T_STAGES) / TC_T_STAGES) & 1);
+          if (SH) {                                   // gpos / fround already describe chunk c + 1
+            if (gpos == 0) pre_raw = mbar_test(smem_u32(&bar_raw_full[fround % TC_SH_STAGES]), (fround / TC_SH_STAGES) & 1);
+          } else {
+            pre_raw = mbar_test(smem_u32(&bar_raw_full[nr % TC_A_STAGES]), (nr / TC_A_STAGES) & 1);
+          }
+        }
+        if (WMD_TC_EXP != 3) asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_asplit[ts]));
@@ -875,11 +916,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         if (ih == 0) TC_TRACE(2, 0, c);
         mbar_wait(smem_u32(&bar_b[bs]), (round / TC_B_STAGES) & 1, 0x48000u + round);        // weight image has landed (long ago)
         if (ih == 0) TC_TRACE(2, 1, c);
-        mbar_wait(smem_u32(&bar_asplit[ts]), (round / TC_T_STAGES) & 1, 0x40000u + round);   // split A of this chunk is in TMEM
+        if (WMD_TC_EXP != 4) mbar_wait(smem_u32(&bar_asplit[ts]), (round / TC_T_STAGES) & 1, 0x40000u + round);   // split A of this chunk is in TMEM
         if (ih == 0) TC_TRACE(2, 2, c);
         tc_fence_after();
         const uint64_t b0 = umma_desc_sw128(sB_u + bs * B_IMG);
-        const uint32_t ah = tmem_u + Cfg::A_COL0 + ts * 128u + static_cast<uint32_t>(ih * 64);
+        const uint32_t ah = tmem_u + Cfg::A_COL0 + ts * Cfg::A_STAGE + static_cast<uint32_t>(ih * (Cfg::A_STAGE / 2));
         if (elect_one()) {
           if (F16) {
             // rows of the weight tile: [h1: 64 B | h2: 64 B]; a k-step is 16 channels = 32 B; A: h1 columns 0..15, h2 16..31
@@ -995,62 +1036,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       }
       __syncthreads();
       const int nseg = s_fixup;
-      const int m = m0 + my_row;
-      if (nseg > 0 && m < rows) {
+      if (nseg > 0) {
         __threadfence();
-        const float* pb = partial + kBalCounterBytes / 4 + (rem_t * plan.slabs * TC_BM + my_row) * BN + my_ch * ACC;
-        float* yr = d.y + static_cast<long long>(m) * d.ldy;
-        // tf32 form: bias first, then the slabs (the order of every earlier version); f16 form: slabs, scale, bias.
-        // Eight quads at a time: their slab loads are independent (L2 latency is paid once per group, not per quad)
-        constexpr int kGroup = ACC < 32 ? ACC : 32;
-#pragma unroll 1
-        for (int j0 = 0; j0 < ACC; j0 += kGroup) {
-          float4 v[kGroup / 4], bq[kGroup / 4];
+        // Cooperative and coalesced: the slabs are row-major [256][BN], so consecutive threads take consecutive float4s
+        // (a warp reads 512 contiguous bytes per slab and writes 512 contiguous bytes of one output row); four quads per
+        // thread are in flight, i.e. 4 x nseg independent L2 loads instead of one dependent load per quad.
+        // tf32 form: bias first, then the slabs in slab order (the order of every earlier version); f16: slabs, scale, bias.
+        const float* pb = partial + kBalCounterBytes / 4 + rem_t * plan.slabs * TC_BM * BN;
+        constexpr int kQuadsPerRow = BN / 4;
+        constexpr int kQuads = TC_BM * kQuadsPerRow;
+        constexpr int kUnroll = 4;
+        static_assert(kQuads % (TC_THREADS * kUnroll) == 0, "quads of a tile divide evenly");
+        const int tile_rows = min(TC_BM, rows - m0);
+        const float ap = d.act_param;
+        for (int base = tid; base < kQuads; base += TC_THREADS * kUnroll) {
+          float4 v[kUnroll], bq[kUnroll];
+          int r[kUnroll], co[kUnroll];
+          bool live[kUnroll];
 #pragma unroll
-          for (int q = 0; q < kGroup / 4; ++q) {
-            const int co = n0 + my_ch * ACC + j0 + 4 * q;
+          for (int q = 0; q < kUnroll; ++q) {
+            const int idx = base + q * TC_THREADS;
+            r[q] = idx / kQuadsPerRow;
+            co[q] = n0 + 4 * (idx % kQuadsPerRow);
+            live[q] = r[q] < tile_rows && co[q] < d.cout;
             bq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (d.bias && co < d.cout) {
-              if (al_ok && co + 3 < d.cout) {
-                bq[q] = __ldg(reinterpret_cast<const float4*>(d.bias + co));
+            if (live[q] && d.bias) {
+              if (al_ok && co[q] + 3 < d.cout) {
+                bq[q] = __ldg(reinterpret_cast<const float4*>(d.bias + co[q]));
               } else {
-                bq[q].x = __ldg(d.bias + co);
-                if (co + 1 < d.cout) bq[q].y = __ldg(d.bias + co + 1);
-                if (co + 2 < d.cout) bq[q].z = __ldg(d.bias + co + 2);
-                if (co + 3 < d.cout) bq[q].w = __ldg(d.bias + co + 3);
+                bq[q].x = __ldg(d.bias + co[q]);
+                if (co[q] + 1 < d.cout) bq[q].y = __ldg(d.bias + co[q] + 1);
+                if (co[q] + 2 < d.cout) bq[q].z = __ldg(d.bias + co[q] + 2);
+                if (co[q] + 3 < d.cout) bq[q].w = __ldg(d.bias + co[q] + 3);
               }
             }
             v[q] = F16 ? make_float4(0.f, 0.f, 0.f, 0.f) : bq[q];
           }
           for (int sidx = 0; sidx < nseg; ++sidx) {
-            const float4* ps = reinterpret_cast<const float4*>(pb + static_cast<long long>(sidx) * TC_BM * BN + j0);
+            const float4* ps = reinterpret_cast<const float4*>(pb + static_cast<long long>(sidx) * TC_BM * BN) + base;
 #pragma unroll
-            for (int q = 0; q < kGroup / 4; ++q) {
-              const float4 pq = __ldcg(ps + q);
-              v[q].x += pq.x; v[q].y += pq.y; v[q].z += pq.z; v[q].w += pq.w;
+            for (int q = 0; q < kUnroll; ++q) {
+              if (live[q]) {
+                const float4 pq = __ldcg(ps + q * TC_THREADS);
+                v[q].x += pq.x; v[q].y += pq.y; v[q].z += pq.z; v[q].w += pq.w;
+              }
             }
           }
 #pragma unroll
-          for (int q = 0; q < kGroup / 4; ++q) {
-            const int co = n0 + my_ch * ACC + j0 + 4 * q;
-            if (co < d.cout) {
+          for (int q = 0; q < kUnroll; ++q) {
+            if (live[q]) {
               float4 o = v[q];
               if (F16) {
                 o.x = __fadd_rn(__fmul_rn(o.x, out_scale), bq[q].x); o.y = __fadd_rn(__fmul_rn(o.y, out_scale), bq[q].y);
                 o.z = __fadd_rn(__fmul_rn(o.z, out_scale), bq[q].z); o.w = __fadd_rn(__fmul_rn(o.w, out_scale), bq[q].w);
               }
-              o.x = activate(o.x, d.act, d.act_param); o.y = activate(o.y, d.act, d.act_param);
-              o.z = activate(o.z, d.act, d.act_param); o.w = activate(o.w, d.act, d.act_param);
+              o.x = activate(o.x, d.act, ap); o.y = activate(o.y, d.act, ap);
+              o.z = activate(o.z, d.act, ap); o.w = activate(o.w, d.act, ap);
+              float* yq = d.y + static_cast<long long>(m0 + r[q]) * d.ldy + co[q];
               out_max = fmaxf(out_max, fabsf(o.x));
-              if (co + 1 < d.cout) out_max = fmaxf(out_max, fabsf(o.y));
-              if (co + 2 < d.cout) out_max = fmaxf(out_max, fabsf(o.z));
-              if (co + 3 < d.cout) out_max = fmaxf(out_max, fabsf(o.w));
-              if (co + 3 < d.cout) {                   // balanced mode requires ldy % 4 == 0 and a 16-byte aligned y
-                *reinterpret_cast<float4*>(yr + co) = o;
+              if (co[q] + 3 < d.cout) {                // balanced mode requires ldy % 4 == 0 and a 16-byte aligned y
+                out_max = fmaxf(fmaxf(out_max, fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w)));
+                *reinterpret_cast<float4*>(yq) = o;
               } else {
-                yr[co] = o.x;
-                if (co + 1 < d.cout) yr[co + 1] = o.y;
-                if (co + 2 < d.cout) yr[co + 2] = o.z;
+                yq[0] = o.x;
+                if (co[q] + 1 < d.cout) { yq[1] = o.y; out_max = fmaxf(out_max, fabsf(o.y)); }
+                if (co[q] + 2 < d.cout) { yq[2] = o.z; out_max = fmaxf(out_max, fabsf(o.z)); }
               }
             }
           }
@@ -1059,7 +1109,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     }
     if (d.amax_out) {                              // max |y| of the layer for its consumers' operand scaling (order independent)
       for (int o = 16; o > 0; o >>= 1) out_max = fmaxf(out_max, __shfl_xor_sync(0xffffffffu, out_max, o));
-      if (lane == 0 && out_max > 0.f) atomicMax(reinterpret_cast<unsigned*>(d.amax_out), __float_as_uint(out_max));
+      if (lane == 0 && out_max > __ldcg(d.amax_out)) atomicMax(reinterpret_cast<unsigned*>(d.amax_out), __float_as_uint(out_max));   // most warps skip the atomic
     }
     TC_TILE_TRACE(6);
     tc_fence_before();
@@ -1178,7 +1228,7 @@ __global__ void absmax_kernel(const float* __restrict__ x, long long count, floa
   const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += step) m = fmaxf(m, fabsf(__ldg(x + i)));
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned*>(out), __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && m > __ldcg(out)) atomicMax(reinterpret_cast<unsigned*>(out), __float_as_uint(m));
 }
 
 // header word 0 holds max |w| when this runs; it is replaced by 1 / s_w by the last block... no: by a second tiny kernel

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restri
   }
   if (amax) {                                    // max |x| of the map, for the consumers' fp16 operand scaling
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(vmax));
+    if (lane == 0 && vmax > __ldcg(amax)) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(vmax));   // most warps skip the atomic
   }
   __syncthreads();
   const int q = lane & 7;                        // channel quad of this lane
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) gather_rows_list_kernel(const float* __re
   }
   if (amax) {                                    // max |x| of the gathered rows, for the consumer's fp16 operand scaling
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(vmax));
+    if (lane == 0 && vmax > __ldcg(amax)) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(vmax));   // most warps skip the atomic
   }
 }
 
@@ -276,6 +276,18 @@ extern "C" int wmd_nchw_to_rows_gated_f32(const float* src, float* dst, const ui
   dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
   WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
   nchw_to_rows_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, dst, gate, C, HW, ld, nullptr);
+  return launched();
+}
+
+extern "C" int wmd_nchw_to_rows_gated_amax_f32(const float* src, float* dst, const uint8_t* gate, int N, int C,
+                                               long long HW, int ld, float* amax, wmd_stream_t stream) {
+  using namespace wmd;
+  WMD_REQUIRE(src && dst && gate, WMD_ERR_ARG);
+  WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
+  if (N == 0) return WMD_OK;
+  dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
+  WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
+  nchw_to_rows_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, dst, gate, C, HW, ld, amax);
   return launched();
 }
 

@@ -342,7 +342,7 @@ class _WaveDecoderBase(nn.Module):
                     skip_rows = ops.gather_rows_list(skip, pix3, off3[n:], amax=slot(i))
                 skip_amax = slot(i)
             else:
-                skip_amax = slot(i) if skip_gate is None else None      # the gated move leaves rows unwritten: no maximum
+                skip_amax = slot(i)
                 if side is not None:
                     skip_rows, skip_done = ops.nchw_to_rows(skip, stream=side, gate=skip_gate, amax=skip_amax)
                 else:

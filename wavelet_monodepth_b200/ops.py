@@ -395,6 +395,9 @@ def nchw_to_rows(x, ld=None, stream=None, gate=None, amax=None):
                 rc = lib.wmd_nchw_to_rows_amax_f32(_lib.ptr(x), _lib.ptr(rows), n, c, h * w, ld, _lib.ptr(amax, _f32), _lib.stream_ptr())
             elif gate is None:
                 rc = lib.wmd_nchw_to_rows_f32(_lib.ptr(x), _lib.ptr(rows), n, c, h * w, ld, _lib.stream_ptr())
+            elif amax is not None:
+                rc = lib.wmd_nchw_to_rows_gated_amax_f32(_lib.host_ptr(x, _f32), _lib.ptr(rows), _lib.ptr(gate), n, c, h * w, ld,
+                                                         _lib.ptr(amax, _f32), _lib.stream_ptr())
             else:
                 rc = lib.wmd_nchw_to_rows_gated_f32(_lib.host_ptr(x, _f32), _lib.ptr(rows), _lib.ptr(gate), n, c, h * w, ld,
                                                     _lib.stream_ptr())
