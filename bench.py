@@ -208,7 +208,8 @@ def conv_layer_table(records, peak_gbs, tf32_peak, steps):
         by, fl = account(name, info)
         rows = min(_as_int(info["count"], info["n"] * info["h"] * info["w"]), info["max_rows"])
         tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        line = {"engine": "tcgen05_3xtf32" if name == "conv_rows_tc" else "fp32_fma", "taps": info["taps"],
+        line = {"engine": ("tcgen05_f16x3" if info.get("f16") else "tcgen05_3xtf32") if name == "conv_rows_tc" else "fp32_fma",
+                "taps": info["taps"],
                 "cin": [info["c0"], info["c1"]], "cout": info["cout"], "grid": [info["n"], info["h"], info["w"]],
                 "rows": rows, "us": round(1e3 * ms, 1), "fp32_eq_tflops": round(tf, 1),
                 "hbm_frac": round(by / (ms * 1e-3) / 1e9 / peak_gbs, 3) if ms > 0 else 0.0}
@@ -248,6 +249,9 @@ def roofline_from(records, peak_gbs, peak_tf, peak_src, steps, peak_tf_sustained
     dom = max(agg, key=lambda k: agg[k]["ms"])
     hbm_view = dict(out[dom])
     tf32 = tf32_peak if tf32_peak else peak_tf / 2.0
+    f16_form = any(n == "conv_rows_tc" and i.get("f16") for n, _, i in records)
+    if f16_form:                       # WMD_CONV_PRECISION=f16x3: the MMAs run at the fp16 rate, so that is the peak
+        tf32, tf32_peak = peak_tf, None
     if dom == "conv_rows_tc":
         alg = hbm_view["tflops"]
         main = {"bound": "tensor", "achieved": round(alg, 1), "peak": round(tf32, 1), "unit": "TFLOP/s",
@@ -263,6 +267,7 @@ def roofline_from(records, peak_gbs, peak_tf, peak_src, steps, peak_tf_sustained
                                       "bf16_sustained_over_2": round(peak_tf_sustained / 2.0, 1) if peak_tf_sustained else None},
                 "peak_source": ("measured in this run: cuBLAS TF32 GEMM 8192^3, best of 20 (burst; each launch is timed alone "
                                 "between two events)" if tf32_peak else peak_src + ": bf16_tflops / 2"),
+                "operand_form": "f16x3 (fp16 pairs, opt-in)" if f16_form else "tf32x3",
                 "note": "achieved = algorithmic fp32-equivalent flops (2*taps*Cin*Cout*M_out) / event time. tcgen05.mma.kind::tf32, "
                         "3 MMAs per fp32 product (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM drained every 1024 of K; "
                         "per-layer figures in conv_layers, DESIGN.md 4"}

@@ -14,6 +14,16 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from wavelet_monodepth_b200 import build as wbuild   # noqa: E402
 
+if sys.argv[1] == "flags":        # python scripts/tc_ablate.py flags <name> "<nvcc -D flags>"  ->  _bin/libwmd_<name>.so
+    out = os.path.join(REPO, "scripts", "bench_cu", "_bin")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libwmd_%s.so" % sys.argv[2])
+    cmd = [wbuild.nvcc_path()] + sys.argv[3].split() + wbuild.NVCC_FLAGS + ["-I", os.path.join(REPO, "include"), "-I", wbuild.CSRC,
+                                                                          "-o", lib] + wbuild.sources()
+    subprocess.run(cmd, check=True)
+    print(lib)
+    sys.exit(0)
+
 if sys.argv[1] == "build":
     out = os.path.join(REPO, "scripts", "bench_cu", "_bin")
     os.makedirs(out, exist_ok=True)

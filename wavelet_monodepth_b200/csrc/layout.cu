@@ -11,46 +11,74 @@ constexpr int kTT = 32;
 // requests; write side: 8 lanes cover the 32 channels of one pixel as float4 (one full 128-byte
 // line per pixel).  The 129-float row pitch makes the transposed shared-memory reads conflict-free.
 constexpr int kTP = 128;   // pixels per tile
-static_assert(kTP / 32 == 4, "the gated variant ORs four group masks");
+// Tile of the two streaming moves (nchw_to_rows, gather_rows_list): LC channels x LP pixels, template parameters.  The read
+// side is contiguous along pixels (LP * 4 bytes per channel row), the write side along channels (LC * 4 bytes per pixel
+// row).  Measured on B200 (scripts/layout_bench.py, bench shapes): the dense transpose is fastest at 32 x 128 (4.0 / 5.9
+// TB/s on f4 / skip4), the list gather at 128 x 32 (2.0 -> 2.5 TB/s at level 2, 1.6 -> 1.8 at level 1).
+template <int LC, int LP>
+struct LayoutTile {
+  static constexpr int kLQ = LC / 4;             // float4 lanes that cover one pixel row of the tile
+  static constexpr int kPPW = 32 / kLQ;          // pixel rows one warp store instruction covers
+  static_assert(LC % 4 == 0 && kLQ <= 32 && 32 % kLQ == 0 && LP % 32 == 0 && LP % (8 * kPPW) == 0, "tile shape");
+  static_assert(sizeof(float) * LC * (LP + 1) + 8 * LP <= 48 * 1024 - 64, "static shared memory");
+};
+constexpr int kDenseLC = 32, kDenseLP = 128;     // nchw_to_rows (plain and gated)
+constexpr int kListLC = 128, kListLP = 32;       // gather_rows_list
 //
 // GATED: `gate` (N, HW) bytes marks the pixels whose rows a later kernel will read (the sparse decoder reads a skip
 // map only under its upsample mask - sparse_upsample, KITTI/layers.py:500).  Reads are skipped per 32-pixel group
 // (one 128-byte request) with no marked pixel, writes per unmarked pixel (one 128-byte line), and a tile with no
 // marked pixel returns after one 128-byte look at the gate; unmarked rows of dst are left untouched.
-template <bool GATED>
+template <bool GATED, int kLC, int kLP>
 __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                            const uint8_t* __restrict__ gate, int C, long long HW,
                                                            int ld, float* __restrict__ amax) {
-  __shared__ float tile[kTT][kTP + 1];
-  __shared__ unsigned marked[kTP / 32];
+  constexpr int kLQ = LayoutTile<kLC, kLP>::kLQ, kPPW = LayoutTile<kLC, kLP>::kPPW;
+  __shared__ float tile[kLC][kLP + 1];
+  __shared__ unsigned marked[kLP / 32];
   const int n = blockIdx.z;
-  const long long p0 = static_cast<long long>(blockIdx.x) * kTP;
-  const int c0 = blockIdx.y * kTT;
+  const long long p0 = static_cast<long long>(blockIdx.x) * kLP;
+  const int c0 = blockIdx.y * kLC;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (GATED) {
-    if (warp < kTP / 32) {
+    if (warp < kLP / 32) {
       const long long p = p0 + 32 * warp + lane;
       const bool on = p < HW && gate[static_cast<long long>(n) * HW + p] != 0;
       const unsigned m = __ballot_sync(0xffffffffu, on);
       if (lane == 0) marked[warp] = m;
     }
     __syncthreads();
-    if ((marked[0] | marked[1] | marked[2] | marked[3]) == 0u) return;
+    unsigned any = 0u;
+#pragma unroll
+    for (int j = 0; j < kLP / 32; ++j) any |= marked[j];
+    if (any == 0u) return;
   }
   const float* s = src + static_cast<long long>(n) * C * HW;
   float* d = dst + static_cast<long long>(n) * HW * ld;
   float vmax = 0.f;
+  // all loads of the thread are issued before the first one is used: predicates only, no branch between two loads (a
+  // `continue` per skipped group made every load wait for the previous one's shared-memory store - 4x slower than the
+  // plain transpose at 35 % density)
+  bool want[kLP / 32];
 #pragma unroll
-  for (int r = warp; r < kTT; r += 8) {
-    const int c = c0 + r;
+  for (int j = 0; j < kLP / 32; ++j) want[j] = !GATED || marked[j] != 0u;
+  float v[kLC / 8][kLP / 32];
+#pragma unroll
+  for (int i = 0; i < kLC / 8; ++i) {
+    const int c = c0 + warp + 8 * i;
     const float* row = s + static_cast<long long>(c) * HW;
 #pragma unroll
-    for (int j = 0; j < kTP / 32; ++j) {          // four fully coalesced 128-byte requests per channel row
-      if (GATED && marked[j] == 0u) continue;
+    for (int j = 0; j < kLP / 32; ++j) {          // fully coalesced 128-byte requests along the channel row
       const long long p = p0 + lane + 32 * j;
-      const float v = (c < C && p < HW) ? __ldg(row + p) : 0.f;
-      tile[r][lane + 32 * j] = v;
-      vmax = fmaxf(vmax, fabsf(v));
+      v[i][j] = (want[j] && c < C && p < HW) ? __ldg(row + p) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLC / 8; ++i) {
+#pragma unroll
+    for (int j = 0; j < kLP / 32; ++j) {
+      tile[warp + 8 * i][lane + 32 * j] = v[i][j];
+      vmax = fmaxf(vmax, fabsf(v[i][j]));
     }
   }
   if (amax) {                                    // max |x| of the map, for the consumers' fp16 operand scaling
@@ -58,11 +86,11 @@ __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restri
     if (lane == 0 && vmax > __ldcg(amax)) atomicMax(reinterpret_cast<unsigned*>(amax), __float_as_uint(vmax));   // most warps skip the atomic
   }
   __syncthreads();
-  const int q = lane & 7;                        // channel quad of this lane
+  const int q = lane % kLQ;                      // channel quad of this lane
   const bool vec_out = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d) & 15) == 0);
 #pragma unroll
-  for (int it = 0; it < kTP / 32; ++it) {
-    const int pl = it * 32 + warp * 4 + (lane >> 3);          // pixel within the tile
+  for (int it = 0; it < kLP / (8 * kPPW); ++it) {
+    const int pl = it * 8 * kPPW + warp * kPPW + lane / kLQ;  // pixel within the tile
     const long long p = p0 + pl;
     const int c = c0 + 4 * q;
     if (GATED && ((marked[pl >> 5] >> (pl & 31)) & 1u) == 0u) continue;
@@ -148,21 +176,23 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 // warp then reads one channel of the 128 pixels as four requests (consecutive list entries are mostly consecutive pixels:
 // 128-byte requests inside a run) and the write side covers each row's 32 channels with eight float4 lanes (one full
 // 128-byte line per row).  Columns C..ld-1 are zero-filled.  src may be pinned host memory.
+template <int kLC, int kLP>
 __global__ void __launch_bounds__(256) gather_rows_list_kernel(const float* __restrict__ src, float* __restrict__ rows,
                                                                int ld, int C, const int32_t* __restrict__ pixels,
                                                                const int32_t* __restrict__ count, int max_rows,
                                                                unsigned HW, float* __restrict__ amax) {
-  __shared__ float tile[kTT][kTP + 1];
-  __shared__ long long base[kTP];
+  constexpr int kLQ = LayoutTile<kLC, kLP>::kLQ, kPPW = LayoutTile<kLC, kLP>::kPPW;
+  __shared__ float tile[kLC][kLP + 1];
+  __shared__ long long base[kLP];
   float vmax = 0.f;                              // (n*C)*HW + yx of the tile's pixels, -1 past the list
   const int M = count ? min(*count, max_rows) : max_rows;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ctiles = (ld + kTT - 1) / kTT;
-  const long long tiles = static_cast<long long>((M + kTP - 1) / kTP) * ctiles;
+  const int ctiles = (ld + kLC - 1) / kLC;
+  const long long tiles = static_cast<long long>((M + kLP - 1) / kLP) * ctiles;
   for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const int m0 = static_cast<int>(t / ctiles) * kTP;
-    const int c0 = static_cast<int>(t % ctiles) * kTT;
-    if (threadIdx.x < kTP) {
+    const int m0 = static_cast<int>(t / ctiles) * kLP;
+    const int c0 = static_cast<int>(t % ctiles) * kLC;
+    if (threadIdx.x < kLP) {
       const int mm = m0 + static_cast<int>(threadIdx.x);
       long long b = -1;
       if (mm < M) {
@@ -174,11 +204,11 @@ __global__ void __launch_bounds__(256) gather_rows_list_kernel(const float* __re
     }
     __syncthreads();
 #pragma unroll
-    for (int r = warp; r < kTT; r += 8) {
+    for (int r = warp; r < kLC; r += 8) {
       const int c = c0 + r;
       const long long coff = static_cast<long long>(c) * HW;
 #pragma unroll
-      for (int j = 0; j < kTP / 32; ++j) {
+      for (int j = 0; j < kLP / 32; ++j) {
         const long long b = base[lane + 32 * j];
         const float v = (c < C && b >= 0) ? __ldg(src + b + coff) : 0.f;
         tile[r][lane + 32 * j] = v;
@@ -186,10 +216,10 @@ __global__ void __launch_bounds__(256) gather_rows_list_kernel(const float* __re
       }
     }
     __syncthreads();
-    const int q = lane & 7;
+    const int q = lane % kLQ;
 #pragma unroll
-    for (int it = 0; it < kTP / 32; ++it) {
-      const int pl = it * 32 + warp * 4 + (lane >> 3);
+    for (int it = 0; it < kLP / (8 * kPPW); ++it) {
+      const int pl = it * 8 * kPPW + warp * kPPW + lane / kLQ;
       const int m = m0 + pl;
       const int c = c0 + 4 * q;
       if (m < M && c < ld)
@@ -261,9 +291,9 @@ extern "C" int wmd_nchw_to_rows_f32(const float* src, float* dst, int N, int C, 
   WMD_REQUIRE(src && dst, WMD_ERR_ARG);
   WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
   if (N == 0) return WMD_OK;
-  dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
+  dim3 grid(ceil_div(HW, kDenseLP), ceil_div(ld, kDenseLC), N);
   WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
-  nchw_to_rows_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, dst, nullptr, C, HW, ld, nullptr);
+  nchw_to_rows_kernel<false, kDenseLC, kDenseLP><<<grid, 256, 0, as_stream(stream)>>>(src, dst, nullptr, C, HW, ld, nullptr);
   return launched();
 }
 
@@ -273,9 +303,9 @@ extern "C" int wmd_nchw_to_rows_gated_f32(const float* src, float* dst, const ui
   WMD_REQUIRE(src && dst && gate, WMD_ERR_ARG);
   WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
   if (N == 0) return WMD_OK;
-  dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
+  dim3 grid(ceil_div(HW, kDenseLP), ceil_div(ld, kDenseLC), N);
   WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
-  nchw_to_rows_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, dst, gate, C, HW, ld, nullptr);
+  nchw_to_rows_kernel<true, kDenseLC, kDenseLP><<<grid, 256, 0, as_stream(stream)>>>(src, dst, gate, C, HW, ld, nullptr);
   return launched();
 }
 
@@ -285,9 +315,9 @@ extern "C" int wmd_nchw_to_rows_gated_amax_f32(const float* src, float* dst, con
   WMD_REQUIRE(src && dst && gate, WMD_ERR_ARG);
   WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
   if (N == 0) return WMD_OK;
-  dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
+  dim3 grid(ceil_div(HW, kDenseLP), ceil_div(ld, kDenseLC), N);
   WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
-  nchw_to_rows_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, dst, gate, C, HW, ld, amax);
+  nchw_to_rows_kernel<true, kDenseLC, kDenseLP><<<grid, 256, 0, as_stream(stream)>>>(src, dst, gate, C, HW, ld, amax);
   return launched();
 }
 
@@ -325,8 +355,8 @@ extern "C" int wmd_gather_rows_list_f32(const float* src_nchw, float* rows, int 
   WMD_REQUIRE((reinterpret_cast<uintptr_t>(rows) & 15) == 0, WMD_ERR_SHAPE);
   WMD_REQUIRE(static_cast<long long>(N) * H * W < (1ll << 31), WMD_ERR_SHAPE);
   if (max_rows == 0 || N == 0) return WMD_OK;
-  const long long tiles = static_cast<long long>(ceil_div(max_rows, kTP)) * ceil_div(ld, kTT);
-  gather_rows_list_kernel<<<stride_grid(tiles * 256, 256, 6), 256, 0, as_stream(stream)>>>(
+  const long long tiles = static_cast<long long>(ceil_div(max_rows, kListLP)) * ceil_div(ld, kListLC);
+  gather_rows_list_kernel<kListLC, kListLP><<<stride_grid(tiles * 256, 256, 6), 256, 0, as_stream(stream)>>>(
       src_nchw, rows, ld, C, pixels, count, max_rows, static_cast<unsigned>(static_cast<long long>(H) * W), nullptr);
   return launched();
 }
@@ -341,8 +371,8 @@ extern "C" int wmd_gather_rows_list_amax_f32(const float* src_nchw, float* rows,
   WMD_REQUIRE((reinterpret_cast<uintptr_t>(rows) & 15) == 0, WMD_ERR_SHAPE);
   WMD_REQUIRE(static_cast<long long>(N) * H * W < (1ll << 31), WMD_ERR_SHAPE);
   if (max_rows == 0 || N == 0) return WMD_OK;
-  const long long tiles = static_cast<long long>(ceil_div(max_rows, kTP)) * ceil_div(ld, kTT);
-  gather_rows_list_kernel<<<stride_grid(tiles * 256, 256, 6), 256, 0, as_stream(stream)>>>(
+  const long long tiles = static_cast<long long>(ceil_div(max_rows, kListLP)) * ceil_div(ld, kListLC);
+  gather_rows_list_kernel<kListLC, kListLP><<<stride_grid(tiles * 256, 256, 6), 256, 0, as_stream(stream)>>>(
       src_nchw, rows, ld, C, pixels, count, max_rows, static_cast<unsigned>(static_cast<long long>(H) * W), amax);
   return launched();
 }
@@ -353,9 +383,9 @@ extern "C" int wmd_nchw_to_rows_amax_f32(const float* src, float* dst, int N, in
   WMD_REQUIRE(src && dst, WMD_ERR_ARG);
   WMD_REQUIRE(N >= 0 && C > 0 && HW > 0 && ld >= C && N <= 65535, WMD_ERR_SHAPE);
   if (N == 0) return WMD_OK;
-  dim3 grid(ceil_div(HW, kTP), ceil_div(ld, kTT), N);
+  dim3 grid(ceil_div(HW, kDenseLP), ceil_div(ld, kDenseLC), N);
   WMD_REQUIRE(grid.y <= 65535, WMD_ERR_SHAPE);
-  nchw_to_rows_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, dst, nullptr, C, HW, ld, amax);
+  nchw_to_rows_kernel<false, kDenseLC, kDenseLP><<<grid, 256, 0, as_stream(stream)>>>(src, dst, nullptr, C, HW, ld, amax);
   return launched();
 }
 

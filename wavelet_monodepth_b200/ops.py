@@ -152,7 +152,9 @@ class _prof:
         if self.start is not None:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
-            _profiler.records.append((self.name, self.start, end, self.info() if self.info else {}))
+            info = self.info() if self.info else {}
+            info["_stream"] = torch.cuda.current_stream().cuda_stream      # for scripts/step_timeline.py
+            _profiler.records.append((self.name, self.start, end, info))
         return False
 
 
