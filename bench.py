@@ -723,7 +723,7 @@ def run_native(args, rank, world, local_rank):
         # further variants: the listed skip map(s) stay in pinned host memory and the gated layout move reads only the
         # 32-pixel groups under the level's upsample mask, in place, across PCIe (graphs captured with gated_layout on)
         was = dec.gated_layout
-        dec.gated_layout = not dec.compact_skip      # compact_skip (default) reads host maps through the list-based gather
+        dec.gated_layout = was or not dec.compact_skip   # compact_skip (default) reads host maps through the list-based gather
         best = None
         try:
             for spec in args.e2e_zero_copy.split(";"):
@@ -870,7 +870,9 @@ def run_native(args, rank, world, local_rank):
                                 "overlapped with the next step, the last one inside the region)",
                 "launch_mode": "CUDA graph replay (graphs.GraphedSparseDecoder)" if use_graph else "eager",
                 "head_1x1_stages": "fused (head_mlp) on levels 2, 1" if dec.fused_heads else "two gather-GEMM launches per level",
-                "layout_moves": ("sparse levels: list-based gather of the upsample-mask pixels only (compact skip rows); dense level: whole maps"
+                "layout_moves": ("sparse levels %s: list-based gather of the upsample-mask pixels only (compact skip rows); other sparse "
+                                 "levels: %s; dense level: whole maps" % (sorted(dec.compact_skip_levels),
+                                                                        "transpose gated by the upsample mask" if dec.gated_layout else "whole maps")
                                  if dec.compact_skip else "%s, %s" % ("gated by the upsample mask" if dec.gated_layout else "whole maps",
                                                                       "side stream" if dec.overlap_layout else "in order")),
             },

@@ -119,7 +119,7 @@ def test_level_masks_bit_exact(n, h, w):
 
 
 @pytest.mark.parametrize("n,h,w,p", [(1, 10, 14, 0.5), (3, 40, 128, 0.2), (2, 31, 67, 0.9), (2, 8, 8, 0.0),
-                                     (4, 160, 512, 0.1), (1, 3, 5, 1.0)])
+                                     (4, 160, 512, 0.1), (1, 3, 5, 1.0), (7, 1, 3, 0.6), (5, 2, 1, 0.5), (33, 3, 3, 0.4)])
 def test_compaction_bit_exact(n, h, w, p):
     rs = np.random.RandomState(15)
     mask = torch.from_numpy((rs.uniform(size=(n, 1, h, w)) < p).astype(np.uint8))

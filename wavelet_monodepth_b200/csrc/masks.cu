@@ -259,17 +259,37 @@ __global__ void __launch_bounds__(kCThreads) compact_fill_kernel(const uint8_t* 
   __syncthreads();
   unsigned row = before + warp_excl[warp] + incl - c;
   if (base < total) {
+    // per-sample offsets: one 64-bit division per thread (not two per pixel); `next` = first pixel of the next sample
+    long long smp = 0, next = 0;
+    if (offsets) {
+      smp = base / HW;
+      next = smp * HW;
+      if (next < base) { ++smp; next += HW; }        // the next sample boundary at or after base
+    }
+    int32_t idx[kCPer];
 #pragma unroll
     for (int k = 0; k < kCPer; ++k) {
       const long long p = base + k;
+      idx[k] = -1;
       if (p < total) {
-        if (offsets && (p % HW) == 0) offsets[p / HW] = static_cast<int32_t>(row);
-        if (idxmap) idxmap[p] = m[k] ? static_cast<int32_t>(row) : -1;
+        if (offsets && p == next) { offsets[smp] = static_cast<int32_t>(row); ++smp; next += HW; }
         if (m[k]) {
+          idx[k] = static_cast<int32_t>(row);
           if (pixels) pixels[row] = static_cast<int32_t>(p);
           ++row;
         }
         if (offsets && p == total - 1) offsets[N] = static_cast<int32_t>(row);
+      }
+    }
+    if (idxmap) {
+      if (base + kCPer <= total && (reinterpret_cast<uintptr_t>(idxmap) & 15) == 0) {   // base is a multiple of 8: 32-byte aligned
+        int4* o = reinterpret_cast<int4*>(idxmap + base);
+        o[0] = make_int4(idx[0], idx[1], idx[2], idx[3]);
+        o[1] = make_int4(idx[4], idx[5], idx[6], idx[7]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kCPer; ++k)
+          if (base + k < total) idxmap[base + k] = idx[k];
       }
     }
   }

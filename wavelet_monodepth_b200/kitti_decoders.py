@@ -165,8 +165,9 @@ class _WaveDecoderBase(nn.Module):
         self.full_res_size = None
         # run the skip maps' layout transposes on a side stream (WMD_OVERLAP_LAYOUT=0/1 sets the default)
         self.overlap_layout = os.environ.get("WMD_OVERLAP_LAYOUT", "0") == "1"
-        # transpose a sparse level's skip map only under its upsample mask (WMD_GATED_LAYOUT=0/1 sets the default)
-        self.gated_layout = os.environ.get("WMD_GATED_LAYOUT", "0") == "1"
+        # transpose a sparse level's skip map only under its upsample mask (WMD_GATED_LAYOUT=0/1 sets the default).  On since
+        # the gated move issues all its loads before using any (72 us against 175 before and ~110 for the whole level-3 map)
+        self.gated_layout = os.environ.get("WMD_GATED_LAYOUT", "1") == "1"
         # run the two 1x1 head stages of the fine levels as one fused kernel (WMD_FUSED_HEADS=0/1 sets the default)
         self.fused_heads = os.environ.get("WMD_FUSED_HEADS", "1") == "1"
         # level 4: the LL head's 3x3 stage rides in the tap-product GEMM of the +/- heads (WMD_FACTORED_LL=0/1)
@@ -180,7 +181,7 @@ class _WaveDecoderBase(nn.Module):
         # ... at the levels where it pays on a device-resident map: measured (scripts/probe_gather.py, B200) the list-based
         # gather moves ~2 TB/s of useful bytes against 6.5 TB/s for the whole-map transpose, so it wins below ~30 % mask
         # density - levels 2 and 1 (16-28 % on the bench), not level 3 (50 %).  A pinned-host skip map always takes it.
-        self.compact_skip_levels = (1, 2)
+        self.compact_skip_levels = tuple(int(v) for v in os.environ.get("WMD_COMPACT_SKIP_LEVELS", "1,2").split(",") if v)
         # tail of every level as one kernel: head gather-sum -> yh -> IDWT -> disp -> next level's threshold
         # (wmd_head_idwt_f32; WMD_FUSED_TAIL=0/1).  Bit-identical to the head_gather + idwt_haar + range_thresh chain.
         self.fused_tail = os.environ.get("WMD_FUSED_TAIL", "1") == "1"
