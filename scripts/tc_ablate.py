@@ -1,10 +1,15 @@
 """Timing ablations of conv_rows_tc (WMD_TC_EXP = k builds; their RESULTS ARE WRONG, only the clock matters).
 
-    python scripts/tc_ablate.py build 1 2 3 4      # here: scripts/bench_cu/_bin/libwmd_exp<k>.so
+    python scripts/tc_ablate.py build 1 2 3 5 6    # here: scripts/bench_cu/_bin/libwmd_exp<k>.so
     WMD_LIB_PATH=scripts/bench_cu/_bin/libwmd_exp1.so WMD_CONV_PRECISION=f16x3 python scripts/conv_layers_env.py   # GPU box
 
- 1 no conversion arithmetic in the f16 split     2 = 1 + no shared-memory row reads     3 = 2 + no tcgen05.wait::st
- 4 issuers do not wait for the split (free-running MMAs: the tensor / weight-stream floor)
+ f16 operand form (WMD_CONV_PRECISION=f16x3):
+   1 no conversion arithmetic in the split     2 = 1 + no shared-memory row reads     3 = 2 + no tcgen05.wait::st
+ epilogue (either form):
+   5 output stores go to a 2 MB window that stays in L2     6 no output stores
+ Only the dense level-4 layers keep their shape under an ablation (later masks depend on the wrong outputs).
+ Measured (B200, R50 1024x320 bs32): upconv(4,1) f16x3 827 us -> 713 (1) -> 641 (2) = (3); tf32x3 920.  1x1 256->576: 134 us ->
+ 134 (5) -> 104 (6): the store instructions cost 22 % of that layer wherever they land, DRAM is not what they wait for.
 """
 import os
 import subprocess

@@ -916,7 +916,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         if (ih == 0) TC_TRACE(2, 0, c);
         mbar_wait(smem_u32(&bar_b[bs]), (round / TC_B_STAGES) & 1, 0x48000u + round);        // weight image has landed (long ago)
         if (ih == 0) TC_TRACE(2, 1, c);
-        if (WMD_TC_EXP != 4) mbar_wait(smem_u32(&bar_asplit[ts]), (round / TC_T_STAGES) & 1, 0x40000u + round);   // split A of this chunk is in TMEM
+        mbar_wait(smem_u32(&bar_asplit[ts]), (round / TC_T_STAGES) & 1, 0x40000u + round);   // split A of this chunk is in TMEM
         if (ih == 0) TC_TRACE(2, 2, c);
         tc_fence_after();
         const uint64_t b0 = umma_desc_sw128(sB_u + bs * B_IMG);
@@ -1000,7 +1000,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
               }
               o.x = actf(o.x); o.y = actf(o.y); o.z = actf(o.z); o.w = actf(o.w);
               out_max = fmaxf(fmaxf(out_max, fabsf(o.x)), fmaxf(fabsf(o.y), fmaxf(fabsf(o.z), fabsf(o.w))));
+#if WMD_TC_EXP == 5                               // ablation: same stores, but into a 2 MB window that stays in L2
+              *reinterpret_cast<float4*>(d.y + ((static_cast<long long>(m) * d.ldy + co) & 0x7FFFCll)) = o;
+#elif WMD_TC_EXP == 6                             // ablation: no store at all (the arithmetic survives through out_max)
+              if (o.x == 123456.f) *reinterpret_cast<float4*>(yr + co) = o;
+#else
               *reinterpret_cast<float4*>(yr + co) = o;
+#endif
             } else if (co < d.cout) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
