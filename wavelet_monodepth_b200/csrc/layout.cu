@@ -10,7 +10,6 @@ constexpr int kTT = 32;
 // Tile = 32 channels x 128 pixels.  Read side: a warp streams 128 pixels of one channel as four coalesced 128-byte
 // requests; write side: 8 lanes cover the 32 channels of one pixel as float4 (one full 128-byte
 // line per pixel).  The 129-float row pitch makes the transposed shared-memory reads conflict-free.
-constexpr int kTP = 128;   // pixels per tile
 // Tile of the two streaming moves (nchw_to_rows, gather_rows_list): LC channels x LP pixels, template parameters.  The read
 // side is contiguous along pixels (LP * 4 bytes per channel row), the write side along channels (LC * 4 bytes per pixel
 // row).  Measured on B200 (scripts/layout_bench.py, bench shapes): the dense transpose is fastest at 32 x 128 (4.0 / 5.9
