@@ -43,9 +43,9 @@ def report(info):
     buf = np.zeros(3 * S * K, dtype=np.int64)
     assert lib.wmd_debug_tc_trace(buf.ctypes.data_as(ctypes.c_void_p)) == 0
     t = buf.reshape(3, S, K)
-    tb = np.zeros(64 * 8, dtype=np.int64)
+    tb = np.zeros(64 * 12, dtype=np.int64)
     assert lib.wmd_debug_tc_tile_trace(tb.ctypes.data_as(ctypes.c_void_p)) == 0
-    tt = tb.reshape(64, 8)
+    tt = tb.reshape(64, 12)
     nch = info["taps"] * (-(-info["c0"] // 32) + -(-info["c1"] // 32))
     rows = int(info["count"][0]) if info["count"] is not None else info["rows"]
     print("launch %d: taps %d cin %d+%d cout %d rows %d, %d chunks/tile, sh=%d" %
@@ -66,6 +66,8 @@ def report(info):
             break
         d = [tt[i, j + 1] - tt[i, j] for j in range(7)]
         print("   tile %d: " % i + "  ".join("%s %d" % (l, v) for l, v in zip(labels, d)) + "   total %d clk" % (tt[i, 7] - tt[i, 0]))
+        print("           tables = init %d + tap tables (thread 0) %d + wait for the other threads %d + slot tables %d" %
+              (tt[i, 8] - tt[i, 0], tt[i, 9] - tt[i, 8], tt[i, 10] - tt[i, 9], tt[i, 1] - tt[i, 10]))
     hi = min(K, nch) - 2
     sel = [c for c in range(3, hi) if c % 32 not in (0, 1, 31)]
     if not sel:

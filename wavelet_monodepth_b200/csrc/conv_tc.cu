@@ -121,7 +121,7 @@ __device__ long long g_trace[3 * kTraceSlots * kTraceChunks];
     g_trace[((role) * kTraceSlots + (slot)) * kTraceChunks + (c)] = clock64(); } while (0)
 // per-tile timeline of CTA 0 (thread 0 = split warp 0): tile top, tables built, first raw A landed, chunk loop done,
 // last epoch complete, drained, stored, end-of-tile barrier passed
-constexpr int kTraceTiles = 64, kTileSlots = 8;
+constexpr int kTraceTiles = 64, kTileSlots = 12;   // slots 8..10: inside the table build (init, tap tables, slot tables)
 __device__ long long g_tile_trace[kTraceTiles * kTileSlots];
 #define TC_TILE_TRACE(slot) do { if (blockIdx.x == 0 && tid == 0 && tile_iter < kTraceTiles) \
     g_tile_trace[tile_iter * kTileSlots + (slot)] = clock64(); } while (0)
@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
       for (int e = tid; e < 2 * 3 * TC_SH_EXTRA; e += TC_THREADS) xtra[e] = kNoRow;
       if (tid < 8) nx[tid] = 0;
     }
+    TC_TILE_TRACE(8);
     // thread t: tile row t % 256, taps [t / 256 * 5, ...): the output pixel is read and decoded once per row, the taps'
     // gate / map lookups are independent loads
     {
@@ -485,34 +486,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         y = static_cast<int>(rem / static_cast<unsigned>(d.W));
         x = static_cast<int>(rem - static_cast<unsigned>(y) * static_cast<unsigned>(d.W));
       }
-      for (int tap = t_lo; tap < t_hi; ++tap) {
-        int32_t o0 = kNoRow, o1 = kNoRow;
-        if (live) {
+      // Two rounds of loads for the thread's (up to) five taps instead of one dependent chain per tap: first every tap's
+      // coordinates and its three look-ups (gate byte, source-0 index map, source-1 index map) are issued together - the maps
+      // are read whether or not the gate turns out to be set, their indices are valid for every in-range coordinate - then
+      // the results are combined.  (One tap at a time cost ~800 clk per tap: 3.3-5.0k clk of a 5-10k clk table build.)
+      constexpr int kTapsPerThread = 5;
+      int qv[kTapsPerThread];                        // source-1 pixel of the tap, -1 = out of range / dead row
+      uint8_t gv[kTapsPerThread];
+      int32_t m0v[kTapsPerThread], m1v[kTapsPerThread];
+#pragma unroll
+      for (int k = 0; k < kTapsPerThread; ++k) {
+        const int tap = t_lo + k;
+        qv[k] = -1;
+        gv[k] = 1;
+        m0v[k] = kNoRow;
+        m1v[k] = kNoRow;
+        if (live && tap < t_hi) {
           int qy = y, qx = x;
           if (d.taps == 9) { qy += tap / 3 - 1; qx += tap % 3 - 1; }
           bool ok = pad_coord(qy, d.H, d.pad_mode);
           ok = pad_coord(qx, d.W, d.pad_mode) && ok;
           if (ok) {
             const int q = (n * d.H + qy) * d.W + qx;
-            if (d.gate && !d.gate[q]) ok = false;
-            if (ok) {
-              o1 = d.map1 ? d.map1[q] : q;          // -1 (not in the compact skip list) = kNoRow
-              int r0;
-              if (aligned_rows) {
-                r0 = m;
-              } else {
-                const int qs = (n * Hs + (qy >> d.shift0)) * Ws + (qx >> d.shift0);
-                r0 = d.map0 ? d.map0[qs] : qs;
-              }
-              if (r0 >= 0) o0 = r0;
+            qv[k] = q;
+            if (d.gate) gv[k] = d.gate[q];
+            m1v[k] = d.map1 ? d.map1[q] : q;        // -1 (not in the compact skip list) = kNoRow
+            if (aligned_rows) {
+              m0v[k] = m;
+            } else {
+              const int qs = (n * Hs + (qy >> d.shift0)) * Ws + (qx >> d.shift0);
+              m0v[k] = d.map0 ? d.map0[qs] : qs;
             }
           }
         }
-        tab0[tap * TC_BM + r] = o0;
-        tab1[tap * TC_BM + r] = o1;
+      }
+#pragma unroll
+      for (int k = 0; k < kTapsPerThread; ++k) {
+        const int tap = t_lo + k;
+        if (tap < t_hi) {
+          const bool ok = qv[k] >= 0 && gv[k] != 0;
+          tab0[tap * TC_BM + r] = (ok && m0v[k] >= 0) ? m0v[k] : kNoRow;
+          tab1[tap * TC_BM + r] = ok ? m1v[k] : kNoRow;
+        }
       }
     }
+    TC_TILE_TRACE(9);
     __syncthreads();
+    TC_TILE_TRACE(10);
     // SH: slot tables of the dx = -1 / +1 taps.  Tap (dy, dx) of tile row r reads source row s; if the centre tap of row
     // r + dx reads the same s (the two output pixels are neighbours in the list) the row is already in slot r + dx of the
     // (chunk, dy) stage, otherwise it becomes an extra (slot 256 + k).  Extras past the capacity switch the whole tile to
@@ -529,12 +549,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
         const int32_t* tb = src ? tab1 : tab0;
         const int32_t sidx = tb[(dy * 3 + 1 + dx) * TC_BM + r];
         uint16_t slot = kZeroSlot;
+        bool extra = false;
         if (sidx >= 0) {
           const int rn = r + dx;
           if (rn >= 0 && rn < TC_BM && tb[(dy * 3 + 1) * TC_BM + rn] == sidx) {
             slot = static_cast<uint16_t>(rn);
           } else {
-            const int k = atomicAdd(&nx[src * 3 + dy], 1);
+            extra = true;
+          }
+        }
+        // a warp's 32 entries share (source, dy, side): ONE shared-memory atomic per warp reserves its extras' slots
+        // (run ends are common in sparse tiles; one atomic per entry serialised on six counters)
+        const unsigned xm = __ballot_sync(0xffffffffu, extra);
+        if (xm) {
+          int base_k = 0;
+          if (lane == __ffs(xm) - 1) base_k = atomicAdd(&nx[src * 3 + dy], __popc(xm));
+          base_k = __shfl_sync(0xffffffffu, base_k, __ffs(xm) - 1);
+          if (extra) {
+            const int k = base_k + __popc(xm & ((1u << lane) - 1u));
             if (k < TC_SH_EXTRA) {
               xtra[(src * 3 + dy) * TC_SH_EXTRA + k] = sidx;
               slot = static_cast<uint16_t>(TC_BM + k);
