@@ -616,3 +616,24 @@ def test_compact_skip_rows_bit_identical_to_dense_skip_rows_device_and_pinned_ho
         del g
     with pytest.raises(kd.WmdError):                       # the dense level's skip map must be on the device
         mod(list(feats[:3]) + [feats[3].cpu().pin_memory(), feats[4]], 0.05)
+
+
+def test_f16x3_operand_form_meets_the_same_parity_bars(monkeypatch):
+    """WMD_CONV_PRECISION=f16x3 (opt-in): fp16-pair operands with per-tensor power-of-two scaling - the tiny sparse golden
+    (reference outputs) and the batched-vs-per-sample oracle comparison hold at the tolerance of the default form, masks
+    and total_ops exact; every tensor-core launch that has its sources' maxima really runs the f16 form."""
+    monkeypatch.setenv("WMD_CONV_PRECISION", "f16x3")
+    seen = []
+    real = ops.conv_rows
+
+    def spy(*a, **kw):
+        seen.append((kw.get("amax0") is not None, a[2].kind, a[2].data16 is not None))
+        return real(*a, **kw)
+    monkeypatch.setattr(kd.ops, "conv_rows", spy)
+    for name in ("kitti_tiny_sparse_thr-1_s0", "kitti_tiny_sparse_thr0.2_s1"):
+        want, meta = load_golden(name)
+        mod, _ = _kitti(kd.SparseDepthWaveProgressiveDecoder, meta)
+        got = mod(kitti_features(meta, DEV), meta["thresh_ratio"])
+        compare_outputs(got, want, name + " f16x3")
+    tc = [s for s in seen if s[1] == "tc"]
+    assert tc and all(has_amax and has16 for has_amax, _, has16 in tc), tc

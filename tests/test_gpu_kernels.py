@@ -517,3 +517,51 @@ def test_f16x3_conv_matches_fp64_reference_across_magnitudes(n, cin, c1, cout, h
     e16, e32 = rel_err(got16, want), rel_err(got32, want)
     assert e16 <= 1e-5 and e16 <= 2 * e32 + 1e-6, (e16, e32)        # both carry the truncating accumulation's bias
     assert abs(float(am[2]) - float(got16.abs().max())) <= 1e-6 * float(got16.abs().max())
+
+
+def test_conv_epilogue_elu_matches_expm1_over_the_whole_range():
+    """The tensor-core engine's ELU uses a short branch-free e^v - 1 (Taylor above -0.25, 2^(v log2 e) - 1 on the SFU below):
+    an identity 1x1 convolution passes x through to 22 bits (hi + tf32(lo)), so y - ELU(x) is the activation's own error
+    plus that: < 5e-7 absolute for x <= 0, including both sides of the -0.25 switch and large negatives."""
+    c = 128
+    n, h, w = 1, 8, 64
+    x = torch.empty(n, c, h, w)
+    flat = x.view(-1)
+    g = torch.Generator().manual_seed(5)
+    flat.copy_(torch.cat([torch.linspace(-30.0, 4.0, flat.numel() // 2),
+                          -torch.rand(flat.numel() // 4, generator=g) * 0.6,                 # dense around the switch
+                          torch.rand(flat.numel() - flat.numel() // 2 - flat.numel() // 4, generator=g) * 2e-3 - 1e-3]))
+    flat[:4] = torch.tensor([-0.25, -0.2500001, -0.2499999, -88.0])
+    wt = torch.eye(c).reshape(c, c, 1, 1)
+    wp = ops.pack_weight(wt.to(DEV), 0, kind="tc")
+    assert wp.kind == "tc"
+    y = ops.conv_rows(ops.nchw_to_rows(x.to(DEV)), c, wp, None, c, n, h, w, taps=1, act=ACT_ELU)
+    got = ops.rows_to_nchw(y, n, c, h, w).cpu().double()
+    want = torch.where(x > 0, x.double(), torch.expm1(x.double()))
+    err = (got - want).abs()
+    neg = x <= 0
+    # the operands carry 22 mantissa bits (hi + tf32(lo)): 2.4e-7 relative on the input, on top of the activation's own error
+    assert float(err[neg].max()) < 5e-7, float(err[neg].max())
+    assert float((err[~neg] / want[~neg]).max()) < 5e-7
+    near0 = neg & (x.abs() < 0.2) & (x != 0)
+    assert float((err[near0] / want[near0].abs()).max()) < 6e-7                       # relative where the result is small
+
+
+@pytest.mark.parametrize("n,c,h,w,p", [(2, 70, 12, 40, 0.3), (1, 33, 9, 130, 0.6)])
+def test_layout_moves_report_the_maximum_of_what_they_move(n, c, h, w, p):
+    """amax side channel of the layout moves (operand scaling of the f16x3 form): plain = max |x| of the map, gated = at
+    least the maximum over the marked rows (it covers whole 32-pixel groups), list gather = exactly the listed rows."""
+    x = rnd(n, c, h, w, seed=70) * 37.0
+    rs = np.random.RandomState(71)
+    gate = torch.from_numpy((rs.uniform(size=(n, 1, h, w)) < p).astype(np.uint8)).to(DEV)
+    am = torch.zeros(3, device=DEV)
+    ops.nchw_to_rows(x.to(DEV), amax=am[0:1])
+    rows_g = ops.nchw_to_rows(x.to(DEV), gate=gate, amax=am[1:2])
+    _, pixels, offsets = ops.compact(gate, want_idxmap=False)
+    ops.gather_rows_list(x.to(DEV), pixels, offsets[n:], amax=am[2:3])
+    marked = gate.reshape(-1).bool().cpu()
+    want_rows = x.permute(0, 2, 3, 1).reshape(-1, c)[marked]
+    assert float(am[0]) == float(x.abs().max())
+    assert float(am[2]) == float(want_rows.abs().max())
+    assert float(want_rows.abs().max()) <= float(am[1]) <= float(x.abs().max())
+    assert torch.equal(rows_g[marked.to(DEV)][:, :c].cpu(), want_rows)
