@@ -579,7 +579,7 @@ def run_native(args, rank, world, local_rank):
     n_local, n_global = wl["per_gpu_batch"], wl["per_gpu_batch"] * world
     resident = [f.to(dev) for f in host]
     last = {}
-    gather = shard.OverlappedGather(n_global) if world > 1 else None
+    gather = shard.make_gather(n_global) if world > 1 else None
 
     # serving mode: the launches of one forward captured once in a CUDA graph bound to the resident feature tensors
     # (graphs.py); replay = the same kernels without the per-launch host cost.  --no-graph times the eager calls instead.
@@ -617,7 +617,7 @@ def run_native(args, rank, world, local_rank):
     # the collective alone (N > 1): K all-gathers of disp0 back to back, nothing else on the GPU
     allgather_ms = None
     if world > 1:
-        solo = shard.OverlappedGather(n_global)
+        solo = shard.make_gather(n_global)
         src = out[("disp", 0)]
         hs = []
 
@@ -777,7 +777,7 @@ def run_native(args, rank, world, local_rank):
             graph2 = graphs.GraphedSparseDecoder(dec2, res2, THRESH) if use_graph else None
             lst2 = {}
             st2 = _Stepper(graph2.replay if use_graph else (lambda: dec2(res2, THRESH)),
-                           shard.OverlappedGather(n2) if world > 1 else None, lst2)
+                           shard.make_gather(n2) if world > 1 else None, lst2)
             ms2 = time_device(st2.step, args.steps, max(args.warmup, 3), dist, world, flush=st2.flush)
             o2 = lst2["out"]
             also = {"workload": ALSO, "value": round(n2 * args.steps / (ms2 * 1e-3), 1), "unit": UNIT,
@@ -881,6 +881,11 @@ def run_native(args, rank, world, local_rank):
             "value_channels_last": {"value": round(value_cl, 1), "unit": UNIT, "ms_per_step": round(ms_cl / args.steps, 3),
                                     "note": "same step, encoder features in torch.channels_last: used zero-copy, no layout transposes"},
             "allgather_ms": round(allgather_ms, 3) if allgather_ms is not None else None,
+            "allgather_form": (None if gather is None else
+                               "copy engines over NVLink peer memory (shard.PeerGather: one cudaMemcpyPeerAsync per peer + a 4-byte "
+                               "NCCL all-reduce as the arrival barrier)" if getattr(gather, "_peer", None) not in (None, False) else
+                               "NCCL all_gather_into_tensor (shard.OverlappedGather)%s" %
+                               ("; peer form unavailable: %s" % gather.why_not if getattr(gather, "why_not", None) else "")),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": e2e_h2d * world,
                     "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": round(e2e_ms / args.steps, 3),
                     "pcie_floor_ms": round(e2e_h2d / 57e9 * 1e3, 2),
