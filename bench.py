@@ -557,8 +557,17 @@ def run_native(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    reserved_sms = 0
     if world > 1:
+        # the persistent conv CTAs fill every SM's register file, so the previous step's all-gather kernel can only run in
+        # the gaps between them.  WMD_RESERVED_SMS=n leaves n SMs to it and keeps NCCL to that many CTAs.  Off by default:
+        # one sweep at 4 GPUs (10 steps) gave 4.09 / 3.92 / 4.09 ms per step for n = 0 / 4 / 8 against 3.90 for n = 0 in a
+        # 20-step run - inside the noise, not enough measurements to switch it on
+        reserved_sms = int(os.environ.get("WMD_RESERVED_SMS", "0"))
+        if reserved_sms > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(reserved_sms))
         dist.init_process_group("nccl", device_id=dev)
+        _lib.load().wmd_conv_tc_set_reserved_sms(reserved_sms)
     peak_gbs, peak_tf, peak_src, peak_tf_sus = measured_peaks()
     tf32_peak = measure_tf32_peak(dev)
     section_errors = {}
@@ -881,6 +890,7 @@ def run_native(args, rank, world, local_rank):
             "value_channels_last": {"value": round(value_cl, 1), "unit": UNIT, "ms_per_step": round(ms_cl / args.steps, 3),
                                     "note": "same step, encoder features in torch.channels_last: used zero-copy, no layout transposes"},
             "allgather_ms": round(allgather_ms, 3) if allgather_ms is not None else None,
+            "reserved_sms": reserved_sms,
             "allgather_form": (None if gather is None else
                                "copy engines over NVLink peer memory (shard.PeerGather: one cudaMemcpyPeerAsync per peer + a 4-byte "
                                "NCCL all-reduce as the arrival barrier)" if getattr(gather, "_peer", None) not in (None, False) else

@@ -243,6 +243,12 @@ size_t wmd_conv_tc_splitk_ws_bytes(int max_rows, int ldy, int splits);
  * same rows).  On by default; wmd_conv_tc_set_shared_taps(0) restores one gather per tap (A/B measurements, tests:
  * both forms produce identical bits).  on < 0 only queries.  Returns the previous setting.  Process-wide. */
 int wmd_conv_tc_set_shared_taps(int on);
+/* The tcgen05 engine runs one persistent CTA per SM, and such a CTA holds the SM's whole register file: no other kernel -
+ * an NCCL collective of the previous step in particular - can run beside it.  wmd_conv_tc_set_reserved_sms(n) makes the
+ * persistent grid n CTAs smaller so that n SMs stay free (multi-GPU serving: the all-gather of step k then really runs
+ * under the convolutions of step k + 1).  0 by default; n < 0 only queries.  Returns the previous setting.  Process-wide;
+ * set it before capturing CUDA graphs. */
+int wmd_conv_tc_set_reserved_sms(int n);
 int wmd_conv_rows_tc_splitk_f32(const wmd_conv_desc* d, int splits, void* ws, size_t ws_bytes, wmd_stream_t stream);
 
 /* ---------------------------------------------------------------- coefficient heads (few output channels)

@@ -116,6 +116,7 @@ SIGNATURES = {
     "wmd_gather_rows_list_amax_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                               c_int, c_void_p, c_void_p]),
     "wmd_conv_tc_set_shared_taps": (c_int, [c_int]),
+    "wmd_conv_tc_set_reserved_sms": (c_int, [c_int]),
     "wmd_conv_tc_weight_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "wmd_pack_conv_weight_tc_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "wmd_conv_rows_tc_f32": (c_int, [POINTER(ConvDesc), c_void_p]),

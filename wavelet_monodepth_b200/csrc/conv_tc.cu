@@ -1353,6 +1353,7 @@ static int make_rows_map(CUtensorMap* tm, const float* x, int C, long long rows,
   return rc == CUDA_SUCCESS ? WMD_OK : WMD_ERR_UNSUPPORTED;
 }
 
+static int g_reserved_sms = 0;     // SMs the persistent grid leaves free (for a collective's kernel on multi-GPU runs)
 static int g_shared_taps = 1;      // 3x3 layers: one raw-stage fill per (chunk, dy) shared by the three dx taps (tuning / A-B knob)
 
 template <int BN, bool SH, bool F16>
@@ -1383,7 +1384,7 @@ static int launch_tc(const wmd_conv_desc& d, int splits, float* partial, cudaStr
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const long long tiles = static_cast<long long>(ceil_div(d.max_rows, TC_BM)) * ceil_div(d.cout, BN) * (splits > 0 ? splits : 1);
-  const long long cap = sm_count();
+  const long long cap = sm_count() - g_reserved_sms > 1 ? sm_count() - g_reserved_sms : 1;
   const int grid = splits == 0 ? static_cast<int>(cap) : static_cast<int>(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
   conv_rows_tc_kernel<BN, SH, F16><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(d, d.w, splits, partial, tm0, tm1);
   int rc = launched();
@@ -1408,6 +1409,12 @@ extern "C" int wmd_debug_tc_tile_trace(long long* host_out) {
 #endif
 
 extern "C" int wmd_conv_tc_tile_n(int cout) { return wmd::tc_tile_n(cout); }
+
+extern "C" int wmd_conv_tc_set_reserved_sms(int n) {
+  const int was = wmd::g_reserved_sms;
+  if (n >= 0) wmd::g_reserved_sms = n;
+  return was;
+}
 
 extern "C" int wmd_conv_tc_set_shared_taps(int on) {
   const int was = wmd::g_shared_taps;
