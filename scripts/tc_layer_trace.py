@@ -74,7 +74,7 @@ def report(info):
         return
     for role, nm, lab in ((0, "split warp 0", ["wait raw A", "wait MMA(c-2)", "LDS+split+tcgen05.st", "wait::st + arrive"]),
                           (1, "gather warp 8", ["wait stage free", "issue fill", "-"]),
-                          (2, "issuer 0", ["wait split A", "wait B", "issue 12 MMA + commit (+B load)"])):
+                          (2, "issuer 0", ["wait weight image (B)", "wait split A", "issue MMAs + commit"])):
         x = t[role]
         period = np.mean([x[0, c + 1] - x[0, c] for c in sel])
         parts = ["%s %d" % (lab[i], np.mean([x[i + 1, c] - x[i, c] for c in sel])) for i in range(len(lab))]

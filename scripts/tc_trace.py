@@ -57,7 +57,7 @@ sel = [c for c in range(lo, hi) if c % 32 not in (0, 1, 31)]
 print("%s: %d chunks/tile; clocks per chunk (mean over %d steady chunks)" % (name, nch, len(sel)))
 for role, nm, labels in ((0, "split warp 0", ["wait raw A", "wait MMA(c-2)", "LDS+split+tcgen05.st", "wait::st + arrive", "loop"]),
                          (1, "gather warp 8", ["wait raw stage free", "issue gather c+2", "wait gather c + arrive", "loop"]),
-                         (2, "issuer 0", ["wait split A", "wait B", "issue 12 MMA + commit (+B load)", "loop"])):
+                         (2, "issuer 0", ["wait weight image (B)", "wait split A", "issue MMAs + commit", "loop"])):
     tt = t[role]
     npts = len(labels)
     period = np.mean([tt[0, c + 1] - tt[0, c] for c in sel])
