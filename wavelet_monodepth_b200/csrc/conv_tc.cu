@@ -5,11 +5,15 @@
 // the taps of a channel chunk innermost (their source rows overlap: L2 hits).
 // Warp-specialised, mbarrier-pipelined (no CTA-wide barrier inside the K loop):
 //
-//   gather warps (8-13)
+//   gather warps (8-12)
 //     * implicit im2col by the TMA: `cp.async.bulk.tensor.2d...tile::gather4` fetches the 128-byte channel slice of
 //       four arbitrary source rows (indices from the per-tile tap table; row -1 = inactive / padded tap and the
-//       channel tail are zero-filled by the TMA) into a raw fp32, 128B-swizzled shared tile: 64 loads per chunk,
-//       three raw stages (two chunks in flight while one is being split), completion by mbarrier transaction bytes;
+//       channel tail are zero-filled by the TMA) into a raw fp32, 128B-swizzled shared tile, completion by mbarrier
+//       transaction bytes.  3x3 layers: one fill per (chunk, dy) serves the three dx taps (shared-tap form, below);
+//       1x1 stages over consecutive rows: one tiled load of the whole 256-row box;
+//   weight loader (warp 13)
+//     * B (weights) is pre-split, pre-swizzled by wmd_pack_conv_weight_tc_f32 into one [hi | lo] image per (n-tile,
+//       chunk): a single cp.async.bulk per chunk into a 3- or 4-deep ring, B_STAGES - 1 chunks ahead of the MMAs;
 //   split warps (0-7), thread = tile row = TMEM lane
 //     * read the row's 128 bytes back (the swizzle makes this transposed read conflict-free), split x = hi + lo
 //       (hi = x with the 13 low mantissa bits cleared, lo = x - hi: exact) and write hi / lo into TENSOR MEMORY with
@@ -17,17 +21,21 @@
 //       full 128 B/clk of shared-memory bandwidth three times per k-step;
 //   issuers (warps 14-15, one per M half = one per accumulator)
 //     * whole warp in the loop, one elected lane issues: 4 k-steps x 3 terms (lo*hi + hi*lo + hi*hi) per chunk, then
-//       commits to the mbarriers that recycle the TMEM A stage / shared B stage.  B (weights) is pre-split,
-//       pre-swizzled by wmd_pack_conv_weight_tc_f32 into one [hi | lo] image per (n-tile, chunk): a single
-//       cp.async.bulk per chunk into a 3-deep ring;
+//       commits to the mbarriers that recycle the TMEM A stage / shared B stage;
 //   all 16 warps
 //     * the tensor core's fp32 accumulation rounds toward zero, a bias that grows linearly with K (measured
 //       ~6.5e-9 * K relative).  So accumulation runs in EPOCHS of kFlushChunks chunks: a finished epoch is drained
 //       (tcgen05.ld) into per-thread fp32 registers with round-to-nearest adds and the TMEM accumulators are
-//       re-zeroed.  Each thread ends up owning one output row x N/2 channels: bias + activation + one contiguous store.
-// What bounds it (scripts/tc_trace.py, scripts/bench_cu/*): shared-memory wavefronts.  Per chunk at N=128 the MMAs read
-// B 24 x 4 KB (768 wavefronts), B lands (256), raw A lands (256) and is read back (256): ~1540 clk against ~1620 clk of
-// tensor-pipe work.  The earlier cp.async gather cost ~640 wavefronts per chunk on top and serialised with the split.
+//       re-zeroed.  Each thread ends up owning one output row x N/2 channels: bias + activation (picked once per tile,
+//       vector bias loads: the epilogue is instruction bound) + one contiguous store;
+//     * balanced scheduling (long reductions): whole tiles for the full rounds, the (tile, chunk) units of the remainder
+//       dealt out evenly on the device (stream-K); the last segment of a cut tile to arrive sums all segments in slab
+//       order, cooperatively and coalesced.
+// What bounds it (scripts/tc_layer_trace.py, scripts/tc_ablate.py): the tensor pipe.  24 UTCHMMAs per chunk
+// cost 64 clk each at N = 128 (1536 clk) and ~52 clk at any N <= 64 (an instruction-rate floor); the feed - A 16 KB
+// (shared-tap) + B 32 KB per chunk through an L2 that delivers ~45 B/clk per SM when all SMs stream - fits under it.
+// Optional fp16-pair operand form (F16 = true, wmd_conv_desc.precision): x 2^e = h1 + h2 as fp16, kind::f16 MMAs with K = 16
+// (half the instructions), scale from the sources' max |x| (device scalars), weights' scale in the packed image's header.
 // Shared-tap gather (SH = true, every 3x3 layer): the three dx taps of a (channel chunk, dy) read almost the same source
 // rows - tap dx of tile row r is tap 0 of row r + dx whenever the two output pixels are neighbours in the active list.
 // One raw stage fill per (chunk, dy) therefore serves THREE chunks: slots 0..255 hold the dx = 0 sources of the tile's
@@ -36,8 +44,9 @@
 // L2->SM traffic of the A operand and the TMA gather4 count drop ~3x (measured intake limit: ~45 B/clk/SM, at which
 // re-gathering every tap bounds all layers with N <= 64).  A tile whose extras overflow (isolated pixels: > 128 per
 // (source, dy)) falls back to one fill per chunk with identity slots - same code, group size 1.
-// TMEM map (512 columns): [0,2N) accumulators (half h at h*N), [256,512) A operand: stage s, half h at
-// 256 + s*128 + h*64, hi in the first 32 columns, lo in the next 32.
+// TMEM map (512 columns): [0,2N) accumulators (half h at h*N), [A_COL0,512) A operand: tf32 form stage s, half h at
+// A_COL0 + s*128 + h*64, hi in the first 32 columns, lo in the next 32 (2 stages at N = 128, 3 below); f16 form stage s,
+// half h at A_COL0 + s*64 + h*32, h1 in the first 16 columns, h2 in the next 16 (4 stages).
 #include <cuda_fp16.h>
 #include <cuda.h>   // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
 
@@ -624,12 +633,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_rows_tc_kernel(const wmd_c
     // Implicit im2col through the TMA: every `tile::gather4` load fetches the 128-byte channel slice of FOUR arbitrary
     // source rows (row indices from the tap table; -1 and channels past C are zero-filled by the TMA) into 512
     // contiguous, 128B-swizzled bytes of the raw stage and completes on the stage's mbarrier.  A chunk is 64 loads:
-    // gather warp g issues groups g, g+6, ...  One load costs the issuing warp ~140 clk here - that is the TMA unit's
+    // gather warp g issues groups g, g+5, ...  One load costs the issuing warp ~140 clk here - that is the TMA unit's
     // queue, not the warp.  Everything a load needs except the four row indices is made provably warp-uniform
     // (shuffles), so ptxas keeps it in uniform registers across the unrolled loop; per load that leaves one LDS.128 +
     // four R2URs.
     const uint32_t sA_u = __shfl_sync(0xffffffffu, smem_u32(sA_base), 0);
-    const int gw = warp - TC_SPLIT_WARPS;                               // gather warp index (valid for warps 8-13)
+    const int gw = warp - TC_SPLIT_WARPS;                               // gather warp index (valid for warps 8-12)
     // ---- one-fill-per-chunk form (SH = false): chunk c -> raw stage round % 3, rows = the tap's table
     constexpr int kMaxLoadsPerWarp = (TC_BM / 4 + TC_GATHER_WARPS - 1) / TC_GATHER_WARPS;
     auto gather_chunk = [&](int c, uint32_t round) {
